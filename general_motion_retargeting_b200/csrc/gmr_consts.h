@@ -1,0 +1,119 @@
+// Device-side constant block of one (source format, robot) pair: the flat tables the solve
+// kernel stages into shared memory once per CTA.  Filled on the host by
+// gmr_fill_consts() from a GmrModelDesc (include/gmr_b200.h).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/gmr_b200.h"
+
+#define GMR_NH 32            // lanes of a warp = hinge DoFs (GMR_MAX_HINGE)
+#define GMR_MAX_LEVEL 64
+
+template <typename R>
+struct GmrConsts {
+  int32_t nb, nh, nhum, nt, nlevel, nq, nv, hroot;
+  int32_t use1, use2, max_iter, _pad0;
+  uint32_t in1_mask, in2_mask, limited_mask, foot_mask;
+  R damping, lm, gain, tol, dt, _pad1[3];
+  int16_t parent[GMR_MAX_BODY];       // body -> parent body (-1 root)
+  int16_t bhinge[GMR_MAX_BODY];       // body -> hinge index or -1
+  int16_t lvl_body[GMR_MAX_BODY];     // bodies sorted by tree depth
+  int16_t lvl_off[GMR_MAX_LEVEL + 2]; // lvl_body[lvl_off[l] .. lvl_off[l+1]) is depth l
+  int16_t hbody[GMR_NH];              // hinge -> body
+  int16_t tbody[GMR_MAX_TASK];        // task -> robot body
+  int16_t thuman[GMR_MAX_TASK];       // task -> human body
+  uint32_t anc_mask[GMR_NH];          // hinge i -> bitmask of hinges that are strict ancestors of i
+  uint32_t task_mask[GMR_NH];         // hinge i -> bitmask of tasks whose body lies in i's subtree
+  R bpos[GMR_MAX_BODY * 3];
+  R bquat[GMR_MAX_BODY * 4];
+  R axis[GMR_NH * 3];
+  R lo[GMR_NH], hi[GMR_NH];
+  R qpos0[8 + GMR_NH];
+  R hscale[GMR_MAX_HUMAN];
+  R hpoff[GMR_MAX_HUMAN * 3];
+  R hroff[GMR_MAX_HUMAN * 4];
+  R w1[GMR_MAX_TASK * 2];
+  R w2[GMR_MAX_TASK * 2];
+};
+
+// Validates `d` and fills `c`.  Returns GMR_OK or a negative GMR_E* code; `why` (may be null)
+// receives a static message.
+template <typename R>
+inline int gmr_fill_consts(const GmrModelDesc* d, GmrConsts<R>* c, const char** why) {
+  auto fail = [&](int code, const char* msg) { if (why) *why = msg; return code; };
+  if (!d) return fail(GMR_EINVAL, "null model description");
+  if (d->nbody < 1 || d->nhinge < 0 || d->nhuman < 1 || d->ntask < 1) return fail(GMR_EINVAL, "empty model");
+  if (d->nbody > GMR_MAX_BODY) return fail(GMR_ELIMIT, "too many bodies (GMR_MAX_BODY)");
+  if (d->nhinge > GMR_MAX_HINGE) return fail(GMR_ELIMIT, "too many hinges (GMR_MAX_HINGE)");
+  if (d->nhuman > GMR_MAX_HUMAN) return fail(GMR_ELIMIT, "too many human bodies (GMR_MAX_HUMAN)");
+  if (d->ntask > GMR_MAX_TASK) return fail(GMR_ELIMIT, "too many tasks (GMR_MAX_TASK)");
+  if (!d->body_parent || !d->body_pos || !d->body_quat || !d->body_hinge || !d->qpos0 || !d->human_scale ||
+      !d->human_pos_off || !d->human_rot_off || !d->human_foot || !d->task_body || !d->task_human || !d->task_w1 ||
+      !d->task_w2 || !d->task_in1 || !d->task_in2 || (d->nhinge > 0 && (!d->hinge_axis || !d->hinge_lo || !d->hinge_hi || !d->hinge_limited)))
+    return fail(GMR_EINVAL, "null array in model description");
+  if (d->human_root < 0 || d->human_root >= d->nhuman) return fail(GMR_EINVAL, "human_root out of range");
+  if (!(d->timestep > 0)) return fail(GMR_EINVAL, "timestep must be positive");
+
+  GmrConsts<R>& m = *c;
+  // zero everything (padding included) so the block is reproducible byte for byte
+  { unsigned char* p = reinterpret_cast<unsigned char*>(c); for (size_t i = 0; i < sizeof(GmrConsts<R>); i++) p[i] = 0; }
+  m.nb = d->nbody; m.nh = d->nhinge; m.nhum = d->nhuman; m.nt = d->ntask;
+  m.nq = 7 + d->nhinge; m.nv = 6 + d->nhinge; m.hroot = d->human_root;
+  m.use1 = d->use_stage1 != 0; m.use2 = d->use_stage2 != 0; m.max_iter = d->max_iter;
+  m.damping = R(d->damping); m.lm = R(d->lm_damping); m.gain = R(d->limit_gain); m.tol = R(d->tol); m.dt = R(d->timestep);
+
+  int depth[GMR_MAX_BODY];
+  int maxdepth = 0;
+  for (int b = 0; b < m.nb; b++) {
+    int p = d->body_parent[b];
+    if (b == 0) { if (p != -1) return fail(GMR_EINVAL, "body 0 must be the root (parent -1)"); depth[b] = 0; }
+    else { if (p < 0 || p >= b) return fail(GMR_EINVAL, "bodies must be ordered parent-before-child"); depth[b] = depth[p] + 1; }
+    if (depth[b] > maxdepth) maxdepth = depth[b];
+    m.parent[b] = (int16_t)p;
+    int j = d->body_hinge[b];
+    if (j < -1 || j >= m.nh || (b == 0 && j != -1)) return fail(GMR_EINVAL, "body_hinge out of range");
+    m.bhinge[b] = (int16_t)j;
+    for (int k = 0; k < 3; k++) m.bpos[3 * b + k] = R(d->body_pos[3 * b + k]);
+    for (int k = 0; k < 4; k++) m.bquat[4 * b + k] = R(d->body_quat[4 * b + k]);
+  }
+  if (maxdepth + 1 > GMR_MAX_LEVEL) return fail(GMR_ELIMIT, "kinematic tree too deep");
+  m.nlevel = maxdepth + 1;
+  { int n = 0;
+    for (int l = 0; l <= maxdepth; l++) { m.lvl_off[l] = (int16_t)n; for (int b = 0; b < m.nb; b++) if (depth[b] == l) m.lvl_body[n++] = (int16_t)b; }
+    m.lvl_off[maxdepth + 1] = (int16_t)n; }
+  for (int j = 0; j < m.nh; j++) m.hbody[j] = -1;
+  for (int b = 0; b < m.nb; b++) if (m.bhinge[b] >= 0) {
+    if (m.hbody[m.bhinge[b]] != -1) return fail(GMR_EINVAL, "hinge owned by two bodies");
+    m.hbody[m.bhinge[b]] = (int16_t)b;
+  }
+  int prev_body = 0;
+  for (int j = 0; j < m.nh; j++) {
+    if (m.hbody[j] < 0) return fail(GMR_EINVAL, "hinge without a body");
+    if (m.hbody[j] <= prev_body && j > 0) return fail(GMR_EINVAL, "hinges must be numbered in body order");
+    prev_body = m.hbody[j];
+    for (int k = 0; k < 3; k++) m.axis[3 * j + k] = R(d->hinge_axis[3 * j + k]);
+    m.lo[j] = R(d->hinge_lo[j]); m.hi[j] = R(d->hinge_hi[j]);
+    if (d->hinge_limited[j]) { if (d->hinge_lo[j] > d->hinge_hi[j]) return fail(GMR_EINVAL, "hinge range lo > hi"); m.limited_mask |= 1u << j; }
+    uint32_t anc = 0;
+    for (int b = m.parent[m.hbody[j]]; b >= 0; b = m.parent[b]) if (m.bhinge[b] >= 0) anc |= 1u << m.bhinge[b];
+    m.anc_mask[j] = anc;
+  }
+  for (int i = 0; i < m.nq; i++) m.qpos0[i] = R(d->qpos0[i]);
+  for (int i = 0; i < m.nhum; i++) {
+    m.hscale[i] = R(d->human_scale[i]);
+    for (int k = 0; k < 3; k++) m.hpoff[3 * i + k] = R(d->human_pos_off[3 * i + k]);
+    for (int k = 0; k < 4; k++) m.hroff[4 * i + k] = R(d->human_rot_off[4 * i + k]);
+    if (d->human_foot[i]) m.foot_mask |= 1u << i;
+  }
+  for (int t = 0; t < m.nt; t++) {
+    int b = d->task_body[t], h = d->task_human[t];
+    if (b < 0 || b >= m.nb || h < 0 || h >= m.nhum) return fail(GMR_EINVAL, "task index out of range");
+    m.tbody[t] = (int16_t)b; m.thuman[t] = (int16_t)h;
+    m.w1[2 * t] = R(d->task_w1[2 * t]); m.w1[2 * t + 1] = R(d->task_w1[2 * t + 1]);
+    m.w2[2 * t] = R(d->task_w2[2 * t]); m.w2[2 * t + 1] = R(d->task_w2[2 * t + 1]);
+    if (d->task_in1[t]) m.in1_mask |= 1u << t;
+    if (d->task_in2[t]) m.in2_mask |= 1u << t;
+    for (int bb = b; bb >= 0; bb = m.parent[bb]) if (m.bhinge[bb] >= 0) m.task_mask[m.bhinge[bb]] |= 1u << t;
+  }
+  return GMR_OK;
+}

@@ -1,0 +1,141 @@
+/*
+ * gmr_b200.h — C ABI of the B200-native batched retargeting IK (libgmr_b200.so) and of
+ * its CPU float64 checker (oracle/liboracle.so, gmr_oracle_* symbols).
+ *
+ * The reference has no FFI layer: its boundary for this path is the Python class
+ * `GeneralMotionRetargeting` (reference general_motion_retargeting/__init__.py:3,
+ * general_motion_retargeting/motion_retarget.py:10-185).  The entry points below are what
+ * a binding for that class needs; each cites the reference interface it replaces.
+ * Plain pointers and sizes only; caller owns every buffer; every function returns 0 or a
+ * negative GMR_E* code and never throws or aborts; gmr_last_error() gives the text.
+ */
+#ifndef GMR_B200_H
+#define GMR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GMR_OK            0
+#define GMR_EINVAL       -1   /* bad argument / unsupported model               */
+#define GMR_ECUDA        -2   /* CUDA runtime error (text in gmr_last_error())  */
+#define GMR_ENOMEM       -3
+#define GMR_ELIMIT       -4   /* model exceeds a compiled-in size limit          */
+
+#define GMR_MAX_BODY     64
+#define GMR_MAX_HINGE    32   /* one warp lane per hinge DoF                      */
+#define GMR_MAX_HUMAN    32
+#define GMR_MAX_TASK     32
+
+/* flags for gmr_retarget_batch */
+#define GMR_FLAG_OFFSET_TO_GROUND  1u  /* retarget(..., offset_to_ground=True), motion_retarget.py:122-123,252-270 */
+
+/*
+ * Flat description of one (source format, robot) pair: what the reference constructor
+ * builds from the MJCF (`mj.MjModel.from_xml_path`, motion_retarget.py:27), the IK JSON
+ * (:30-59) and `setup_retarget_configuration` (:74-114), plus the solver knobs the
+ * reference passes to mink (`solver="daqp"`, `damping=0.5` :18-19, `lm_damping=1` :88,
+ * `max_iter=10` :56, threshold 0.001 :153, mink ConfigurationLimit gain 0.95,
+ * `model.opt.timestep` :146).  All arrays are host memory, copied by gmr_model_create.
+ * Quaternions are wxyz.  Bodies are in MuJoCo order without the world body (body 0 = the
+ * floating root); qpos = [x y z qw qx qy qz, hinge...].
+ */
+typedef struct GmrModelDesc {
+  int32_t nbody, nhinge, nhuman, ntask;
+  /* kinematic tree */
+  const int32_t* body_parent;    /* [nbody]  -1 for the root                    */
+  const double*  body_pos;       /* [nbody*3] offset in the parent frame        */
+  const double*  body_quat;      /* [nbody*4]                                   */
+  const int32_t* body_hinge;     /* [nbody]  hinge index owned by body, or -1   */
+  const double*  hinge_axis;     /* [nhinge*3] body-local, unit                 */
+  const double*  hinge_lo;       /* [nhinge]                                    */
+  const double*  hinge_hi;       /* [nhinge]                                    */
+  const uint8_t* hinge_limited;  /* [nhinge]                                    */
+  const double*  qpos0;          /* [7+nhinge]                                  */
+  /* target preprocessing (scale_human_data :209-232, offset_human_data :234-250) */
+  int32_t        human_root;     /* index of human_root_name                    */
+  const double*  human_scale;    /* [nhuman] human_scale_table, before the height ratio */
+  const double*  human_pos_off;  /* [nhuman*3] table-1 pos_offset - ground_height*z (:91) */
+  const double*  human_rot_off;  /* [nhuman*4] table-1 rot_offset, unit (:92)   */
+  const uint8_t* human_foot;     /* [nhuman] name contains "Foot"/"foot" (:260) */
+  /* frame tasks (:80-107): union of table-1 and table-2 entries with a non-zero weight */
+  const int32_t* task_body;      /* [ntask] robot body index (frame_name)       */
+  const int32_t* task_human;     /* [ntask] human body index                    */
+  const double*  task_w1;        /* [ntask*2] position_cost, orientation_cost in stage 1 */
+  const double*  task_w2;        /* [ntask*2] same, stage 2                     */
+  const uint8_t* task_in1;       /* [ntask] member of tasks1                    */
+  const uint8_t* task_in2;       /* [ntask] member of tasks2                    */
+  int32_t        use_stage1, use_stage2;   /* use_ik_match_table1/2 (:51-52)    */
+  /* solver knobs */
+  double  damping;               /* Tikhonov damping passed to mink.solve_ik    */
+  double  lm_damping;            /* FrameTask lm_damping                        */
+  double  limit_gain;            /* ConfigurationLimit gain                     */
+  double  tol;                   /* loop threshold on the error decrease        */
+  double  timestep;              /* model.opt.timestep                          */
+  int32_t max_iter;              /* conditional iterations per stage            */
+} GmrModelDesc;
+
+typedef struct GmrModel GmrModel;  /* opaque; owns device copies of the tables; immutable after create */
+
+/* ---- libgmr_b200.so (CUDA, sm_100a) ----------------------------------------------------- */
+
+/* replaces GeneralMotionRetargeting.__init__ + setup_retarget_configuration
+ * (motion_retarget.py:13-114): validate the description and stage it on `device`. */
+int gmr_model_create(const GmrModelDesc* desc, int device, GmrModel** out);
+int gmr_model_destroy(GmrModel* model);
+
+/* replaces `for frame in frames: qpos = retargeter.retarget(frame)` over a batch of clips
+ * (callers: scripts/smplx_to_robot_dataset.py:84-87, scripts/bvh_to_robot_dataset.py:96-103;
+ * callee: motion_retarget.py:139-185).  All pointers are DEVICE pointers on the model's
+ * device.  Clip c is solved as a fresh retargeter (qpos starts at qpos_init[c] if given,
+ * else qpos0) whose frames t = 0..T-1 are solved in order, each warm-started from the last.
+ *   pos   [C,T,nhuman,3] float32 metres, world Z-up      quat [C,T,nhuman,4] float32 wxyz
+ *   ratio [C] float32 actual_human_height / human_height_assumption (NULL: 1.0)  (:36-43)
+ *   qpos_init [C,nq] or NULL            qpos_out [C,T,nq] float32 (required)
+ *   iters_out [C,T,2] int32 solves per stage, or NULL
+ *   err_out   [C,T,2] float32 final error1()/error2() (:188-200), or NULL
+ *   targets_out [C,T,nhuman,7] float32 = scaled_human_data (pos, quat wxyz) (:124), or NULL
+ * Stream-ordered, asynchronous, no hidden synchronisation. */
+int gmr_retarget_batch(GmrModel* model, const float* pos, const float* quat, const float* ratio,
+                       int32_t C, int32_t T, const float* qpos_init, float* qpos_out,
+                       int32_t* iters_out, float* err_out, float* targets_out,
+                       uint32_t flags, void* cuda_stream);
+
+/* float64 variant of the same kernel (identical semantics; qpos_init/qpos_out/err_out/
+ * targets_out are double).  Exists so that parity can be checked without float32 rounding. */
+int gmr_retarget_batch_f64(GmrModel* model, const float* pos, const float* quat, const float* ratio,
+                           int32_t C, int32_t T, const double* qpos_init, double* qpos_out,
+                           int32_t* iters_out, double* err_out, double* targets_out,
+                           uint32_t flags, void* cuda_stream);
+
+/* Same call with HOST buffers (pinned or pageable): the library chunks the clips, overlaps
+ * H2D copies, the solve and D2H copies on its own streams and returns when qpos_out is
+ * complete.  This is what a dataset script calls. */
+int gmr_retarget_batch_host(GmrModel* model, const float* pos, const float* quat, const float* ratio,
+                            int32_t C, int32_t T, const float* qpos_init, float* qpos_out,
+                            int32_t* iters_out, float* err_out, uint32_t flags);
+
+/* number of kernel launches issued by this library since load (for bench bookkeeping) */
+int64_t gmr_launch_count(void);
+const char* gmr_last_error(void);
+/* static properties of the solve kernel for (model, C): for reports */
+int gmr_kernel_info(GmrModel* model, int32_t precision_bits, int32_t* threads_per_cta,
+                    int32_t* clips_per_cta, int32_t* smem_bytes, int32_t* regs_per_thread,
+                    int32_t* ctas_per_sm);
+
+/* ---- oracle/liboracle.so (CPU checker; test infrastructure only) ----------------------- */
+
+/* Same semantics computed on the host in float64 (precision_bits = 64) or with every
+ * arithmetic step in float32 (32, used to study rounding).  Host pointers.  nthreads <= 0
+ * uses every hardware thread. */
+int gmr_oracle_retarget_batch(const GmrModelDesc* desc, const float* pos, const float* quat,
+                              const float* ratio, int32_t C, int32_t T, const double* qpos_init,
+                              double* qpos_out, int32_t* iters_out, double* err_out,
+                              uint32_t flags, int32_t nthreads, int32_t precision_bits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMR_B200_H */

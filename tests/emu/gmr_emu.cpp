@@ -1,0 +1,56 @@
+// Lane-serial HOST build of the CUDA kernel body (general_motion_retargeting_b200/csrc/
+// gmr_solver.cuh compiled with GMR_EMULATE): a development aid that lets the warp-level
+// algorithm be debugged against the oracle on a machine without a GPU.  It is test
+// infrastructure: nothing in the package loads it and it is never a fallback for the GPU path.
+#define GMR_EMULATE 1
+#include "../../general_motion_retargeting_b200/csrc/gmr_solver.cuh"
+
+#include <atomic>
+#include <thread>
+#include <vector>
+
+template <typename R>
+static int run(const GmrModelDesc* d, const float* pos, const float* quat, const float* ratio, int C, int T,
+               const double* qpos_init, double* qpos_out, int32_t* iters_out, double* err_out, double* tg_out,
+               uint32_t flags, int nthreads, int64_t* refactor_out) {
+  auto* mc = new GmrConsts<R>();
+  const char* why = nullptr;
+  int rc = gmr_fill_consts<R>(d, mc, &why);
+  if (rc != GMR_OK) { delete mc; return rc; }
+  GmrWarpLayout lay = gmr_warp_layout(mc->nb, mc->nh, mc->nhum, mc->nt);
+  if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
+  if (nthreads > C) nthreads = C > 0 ? C : 1;
+  std::atomic<int> next{0};
+  std::atomic<int64_t> refac{0};
+  auto work = [&]() {
+    std::vector<R> sm((size_t)lay.total + 16, R(0));
+    for (;;) {
+      int c = next.fetch_add(1);
+      if (c >= C) break;
+      auto* ws = new WarpSolver<R>(*mc, sm.data());
+      size_t f0 = (size_t)c * T;
+      ws->template run_clip<double>(pos + f0 * mc->nhum * 3, quat + f0 * mc->nhum * 4, ratio ? R(ratio[c]) : R(1), T,
+                                    qpos_init ? qpos_init + (size_t)c * mc->nq : nullptr, qpos_out + f0 * mc->nq,
+                                    iters_out ? iters_out + 2 * f0 : nullptr, err_out ? err_out + 2 * f0 : nullptr,
+                                    tg_out ? tg_out + f0 * mc->nhum * 7 : nullptr, flags);
+      refac += ws->stat_refactor;
+      delete ws;
+    }
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < nthreads; i++) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  if (refactor_out) *refactor_out = refac.load();
+  delete mc;
+  return GMR_OK;
+}
+
+extern "C" int gmr_emu_retarget_batch(const GmrModelDesc* d, const float* pos, const float* quat, const float* ratio,
+                                      int32_t C, int32_t T, const double* qpos_init, double* qpos_out,
+                                      int32_t* iters_out, double* err_out, double* tg_out, uint32_t flags,
+                                      int32_t nthreads, int32_t precision_bits, int64_t* refactor_out) {
+  if (precision_bits == 32)
+    return run<float>(d, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out, tg_out, flags, nthreads, refactor_out);
+  return run<double>(d, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out, tg_out, flags, nthreads, refactor_out);
+}
