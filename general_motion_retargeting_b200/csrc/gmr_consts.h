@@ -36,6 +36,25 @@ struct GmrConsts {
   R w2[GMR_MAX_TASK * 2];
 };
 
+// Scalars of the model that every thread needs all the time.  They travel as kernel
+// parameters (constant bank), so they cost no registers and no shared-memory reads.
+struct GmrDims {
+  int32_t nb, nh, nhum, nt, nlevel, nq, hroot, use1, use2, max_iter;
+  uint32_t in1_mask, in2_mask, limited_mask, foot_mask;
+};
+template <typename R> struct GmrScal { R damping, lm, gain, tol, dt; };
+
+template <typename R> inline GmrDims gmr_dims_of(const GmrConsts<R>& c) {
+  GmrDims d;
+  d.nb = c.nb; d.nh = c.nh; d.nhum = c.nhum; d.nt = c.nt; d.nlevel = c.nlevel; d.nq = c.nq; d.hroot = c.hroot;
+  d.use1 = c.use1; d.use2 = c.use2; d.max_iter = c.max_iter;
+  d.in1_mask = c.in1_mask; d.in2_mask = c.in2_mask; d.limited_mask = c.limited_mask; d.foot_mask = c.foot_mask;
+  return d;
+}
+template <typename R> inline GmrScal<R> gmr_scal_of(const GmrConsts<R>& c) {
+  GmrScal<R> s; s.damping = c.damping; s.lm = c.lm; s.gain = c.gain; s.tol = c.tol; s.dt = c.dt; return s;
+}
+
 // Validates `d` and fills `c`.  Returns GMR_OK or a negative GMR_E* code; `why` (may be null)
 // receives a static message.
 template <typename R>

@@ -17,11 +17,12 @@
 //    dense J^T W^2 J and no shared-memory read-modify-write.
 //  * Row i of H lives in REGISTERS of lane i (static indexing, loops unrolled over the pivot
 //    index); the Cholesky factorisation broadcasts the pivot row from shared memory
-//    (one wavefront per 4 values) instead of shuffling or re-reading lane-private rows.
-//    The 6 floating-base DoFs are factored redundantly by every lane (6x6), so no lane ever
-//    needs a second pass when nv = 6 + nhinge > 32.
-//  * Joint-limit box: exact primal active set (same optimum as the reference's DAQP solve);
-//    the common case (unconstrained step feasible) costs one factorisation.
+//    (one 128-bit wavefront per 4 values) instead of shuffling or re-reading lane-private
+//    rows.  The 6 floating-base DoFs form a 6x6 leading block, so no lane ever needs a
+//    second pass when nv = 6 + nhinge > 32.
+//  * Joint-limit box: exact primal active set (same optimum as the reference's DAQP solve),
+//    working set warm-started from the previous solve; the common case (unconstrained step
+//    feasible) costs one factorisation.
 //
 // The file is written as a sequence of "lane blocks" (GMR_LANES ... GMR_END).  On the GPU a
 // block is straight-line code of one thread followed by __syncwarp(); defining GMR_EMULATE
@@ -38,66 +39,60 @@
 #include <cmath>
 #include <cstring>
 #define GMR_FN inline
+#define GMR_HD inline
 #define GMR_LANES for (int lane = 0; lane < 32; ++lane) { LaneRegs<R>& L = lanes_[lane]; (void)L;
 #define GMR_END }
 #define GMR_UNROLL
+#define GMR_SYNC()
 #else
 #define GMR_FN __device__ __forceinline__
+#define GMR_HD __host__ __device__ inline
 #define GMR_LANES { LaneRegs<R>& L = lanes_; const int lane = lane_; (void)L; (void)lane;
 #define GMR_END } __syncwarp();
 #define GMR_UNROLL _Pragma("unroll")
-#endif
-
-#define GMR_HD  // functions below are templates/inline; host+device qualifiers added per build
-#if !defined(GMR_EMULATE)
-#undef GMR_HD
-#define GMR_HD __host__ __device__
+#define GMR_SYNC() __syncwarp()
 #endif
 
 // ---- shared-memory layout of one warp's state (units: elements of R) -----------------------
 GMR_HD constexpr int gmr_pad4(int n) { return (n + 3) & ~3; }
-// offset of pivot row k in the packed factor storage: row k holds 6 base columns + k hinge columns
-GMR_HD constexpr int gmr_loff(int k) { int o = 0; for (int i = 0; i < k; i++) o += gmr_pad4(6 + i); return o; }
+// offset of pivot row k in the packed factor storage (row k = 6 base columns + k hinge columns,
+// padded to 4): sum_{i<k} pad4(6+i) = 4 * (F(k+8) - F(8)), F(N) = sum_{n<=N} floor(n/4)
+GMR_HD constexpr int gmr_loff(int k) {
+  const int N = k + 8, a = N >> 2, b = N & 3;
+  return 4 * (2 * a * (a - 1) + a * (b + 1) - 6);
+}
 
-struct GmrWarpLayout {
-  int q, xp, xq, sc, tg, sd, red, xs, root, lf, piv, bnd, tk, mt, lfac, total;
+// fixed part
+enum {
+  GS_RED = 0,               // [32] reductions / hand-over scratch
+  GS_XS = 32,               // [40] solution of the last linear solve (base 6, hinges)
+  GS_ROOT = 72,             // [28] whole-tree composite: M(21) g(6) mu
+  GS_LF = 100,              // [28] base 6x6 factor (21, reciprocal diagonal) + y_base(6)
+  GS_PIV = 128,             // [4]
+  GS_BND = 132,             // [32] bound value of pinned hinges
+  GS_LP = 164,              // [9][32] lane-private slots
+  GS_Q = 164 + 9 * 32,      // [40] qpos
+  GS_VAR = 164 + 9 * 32 + 40
 };
-GMR_HD inline GmrWarpLayout gmr_warp_layout(int nb, int nh, int nhum, int nt) {
-  GmrWarpLayout w{};
-  int o = 0;
-  w.q = o;    o += gmr_pad4(7 + nh);
-  w.xp = o;   o += gmr_pad4(3 * nb);
-  w.xq = o;   o += 4 * nb;
-  w.sc = o;   o += gmr_pad4(2 * nh);
-  w.tg = o;   o += 8 * nhum;
-  w.sd = o;   o += 8 * (nh > 0 ? nh : 1);
-  w.red = o;  o += 32;
-  w.xs = o;   o += gmr_pad4(6 + nh);
-  w.root = o; o += 28;
-  w.lf = o;   o += 28;
-  w.piv = o;  o += 4;
-  w.bnd = o;  o += 32;
-  // union: {task kinematics (24/task) + task inertias (28/task)}  vs  packed factor rows
-  w.tk = o; w.mt = o + 24 * nt; w.lfac = o;
-  int a = 52 * nt, b = gmr_loff(nh);
-  o += gmr_pad4(a > b ? a : b);
-  w.total = o;
-  return w;
+enum { LP_F = 0, LP_DIAG = 6, LP_CI = 7, LP_X = 8 };
+
+template <typename R> GMR_HD int gmr_in_elems(int nhum) { return gmr_pad4((int)((8 * nhum * sizeof(float) + sizeof(R) - 1) / sizeof(R))); }
+// variable part: sd[8nh] tg[8nhum] in[staged floats] xp[pad4(3nb)] xq[4nb] U[max(28nt, loff(nh), 64)]
+template <typename R> GMR_HD int gmr_warp_elems(int nb, int nh, int nhum, int nt) {
+  int u = 28 * nt; if (gmr_loff(nh) > u) u = gmr_loff(nh); if (u < 64) u = 64;
+  return GS_VAR + 8 * (nh > 0 ? nh : 1) + 8 * nhum + gmr_in_elems<R>(nhum) + gmr_pad4(3 * nb) + 4 * nb + gmr_pad4(u);
 }
 
 template <typename R> struct GmrEps;
 template <> struct GmrEps<float>  { static constexpr float  lie = 1.1920929e-06f; static constexpr float  lam = 1e-5f;  };
 template <> struct GmrEps<double> { static constexpr double lie = 2.220446049250313e-15; static constexpr double lam = 1e-12; };
 
-// per-lane registers that persist across lane blocks
+// per-lane registers that persist across lane blocks (what the factorisation keeps live;
+// colder per-lane state sits in the lane-private shared-memory slots GS_LP)
 template <typename R> struct LaneRegs {
   R a[6];          // base (floating joint) columns of this hinge's row of H, then of L
   R row[GMR_NH];   // hinge columns j <= lane
   R rhs, dinv, tmp;
-  R f[6];          // Ic_i * s_i
-  R diag, ci;
-  R x, xs, blo, bhi;
-  float in_pos[3]; float in_quat[4];
 };
 
 // ---- tiny math helpers ----------------------------------------------------------------------
@@ -117,6 +112,23 @@ template <> __device__ __forceinline__ float g_sqrt<float>(float x) { return sqr
 template <> __device__ __forceinline__ float g_atan2<float>(float y, float x) { return atan2f(y, x); }
 template <> __device__ __forceinline__ float g_abs<float>(float x) { return fabsf(x); }
 #endif
+
+// 4 consecutive elements from 16-byte aligned shared memory (one LDS.128 / two LDS.128)
+GMR_FN void g_ld4(const float* p, float* v) {
+#ifdef GMR_EMULATE
+  v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[3] = p[3];
+#else
+  const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+#endif
+}
+GMR_FN void g_ld4(const double* p, double* v) {
+#ifdef GMR_EMULATE
+  v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[3] = p[3];
+#else
+  const double2 t = *reinterpret_cast<const double2*>(p), u = *reinterpret_cast<const double2*>(p + 2);
+  v[0] = t.x; v[1] = t.y; v[2] = u.x; v[3] = u.y;
+#endif
+}
 
 template <typename R> GMR_FN void q_mul(const R* a, const R* b, R* o) {
   R w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
@@ -181,56 +193,57 @@ template <typename R> GMR_FN void m3_skew(const R* v, R* S) {
   S[0] = R(0); S[1] = -v[2]; S[2] = v[1]; S[3] = v[2]; S[4] = R(0); S[5] = -v[0]; S[6] = -v[1]; S[7] = v[0]; S[8] = R(0);
 }
 
-// index of (i,j), i<=j, in the packed upper triangle of a symmetric 6x6 (21 entries)
+// index of (i,j) in the packed upper triangle of a symmetric 6x6 (21 entries)
 GMR_HD constexpr int gmr_sym6(int i, int j) { return i <= j ? (i * (13 - i)) / 2 + (j - i) : (j * (13 - j)) / 2 + (i - j); }
 
 // =============================================================================================
 template <typename R>
 struct WarpSolver {
-  const GmrConsts<R>& mc;
+  const GmrConsts<R>& mc;     // per-robot tables (shared memory on the GPU)
+  const GmrDims& dm;          // sizes / masks (kernel parameter: constant bank)
+  const GmrScal<R>& ks;       // solver knobs (kernel parameter)
   R* sm;                      // this warp's shared-memory block
-  GmrWarpLayout lay;
 #ifdef GMR_EMULATE
   LaneRegs<R> lanes_[32];
 #else
   LaneRegs<R> lanes_;
   int lane_;
 #endif
-  // per-solve statistics (uniform)
-  int stat_refactor;
+  int stat_refactor;           // factorisations done (uniform)
   uint32_t warm_lo, warm_hi;   // working set carried from the previous solve (uniform)
 
-  GMR_FN WarpSolver(const GmrConsts<R>& m, R* smem
+  GMR_FN WarpSolver(const GmrConsts<R>& m, const GmrDims& d, const GmrScal<R>& k, R* smem
 #ifndef GMR_EMULATE
                     , int lane
 #endif
-                    ) : mc(m), sm(smem), lay(gmr_warp_layout(m.nb, m.nh, m.nhum, m.nt)), stat_refactor(0), warm_lo(0), warm_hi(0) {
+                    ) : mc(m), dm(d), ks(k), sm(smem), stat_refactor(0), warm_lo(0), warm_hi(0) {
 #ifndef GMR_EMULATE
     lane_ = lane;
 #endif
   }
 
-  GMR_FN R* s_q() const { return sm + lay.q; }
-  GMR_FN R* s_xp() const { return sm + lay.xp; }
-  GMR_FN R* s_xq() const { return sm + lay.xq; }
-  GMR_FN R* s_sc() const { return sm + lay.sc; }
-  GMR_FN R* s_tg() const { return sm + lay.tg; }
-  GMR_FN R* s_sd() const { return sm + lay.sd; }
-  GMR_FN R* s_red() const { return sm + lay.red; }
-  GMR_FN R* s_xs() const { return sm + lay.xs; }
-  GMR_FN R* s_root() const { return sm + lay.root; }
-  GMR_FN R* s_lf() const { return sm + lay.lf; }
-  GMR_FN R* s_piv() const { return sm + lay.piv; }
-  GMR_FN R* s_bnd() const { return sm + lay.bnd; }
-  GMR_FN R* s_tk() const { return sm + lay.tk; }
-  GMR_FN R* s_mt() const { return sm + lay.mt; }
-  GMR_FN R* s_L() const { return sm + lay.lfac; }
+  GMR_FN R* s_red() const { return sm + GS_RED; }
+  GMR_FN R* s_xs() const { return sm + GS_XS; }
+  GMR_FN R* s_root() const { return sm + GS_ROOT; }
+  GMR_FN R* s_lf() const { return sm + GS_LF; }
+  GMR_FN R* s_piv() const { return sm + GS_PIV; }
+  GMR_FN R* s_bnd() const { return sm + GS_BND; }
+  GMR_FN R& lp(int slot, int lane) const { return sm[GS_LP + slot * 32 + lane]; }
+  GMR_FN R* s_q() const { return sm + GS_Q; }
+  GMR_FN R* s_sd() const { return sm + GS_VAR; }
+  GMR_FN R* s_tg() const { return s_sd() + 8 * (dm.nh > 0 ? dm.nh : 1); }
+  GMR_FN float* s_in() const { return reinterpret_cast<float*>(s_tg() + 8 * dm.nhum); }
+  GMR_FN R* s_xp() const { return s_tg() + 8 * dm.nhum + gmr_in_elems<R>(dm.nhum); }
+  GMR_FN R* s_xq() const { return s_xp() + gmr_pad4(3 * dm.nb); }
+  GMR_FN R* s_U() const { return s_xq() + 4 * dm.nb; }
+  GMR_FN R* s_sc() const { return s_U(); }      // half-angle sin/cos, live only inside fk()
+  GMR_FN R* s_mt() const { return s_U(); }      // task inertias, dead once the rows are built
+  GMR_FN R* s_L() const { return s_U(); }       // packed factor rows
 
   // ------------------------------------------------------------------ configuration --------
-  // qpos -> shared memory.  `src` has nq values (uniform pointer); all lanes cooperate.
   template <typename S> GMR_FN void set_qpos(const S* src) {
     GMR_LANES
-      for (int i = lane; i < mc.nq; i += 32) s_q()[i] = R(src[i]);
+      for (int i = lane; i < dm.nq; i += 32) s_q()[i] = R(src[i]);
     GMR_END
   }
 
@@ -238,7 +251,7 @@ struct WarpSolver {
   // then the world-frame spatial axis of every hinge at the root origin -> s_sd[j] = (v, w).
   GMR_FN void fk() {
     GMR_LANES
-      if (lane < mc.nh) {
+      if (lane < dm.nh) {
         R s, c; g_sincos(R(0.5) * s_q()[7 + lane], &s, &c);
         s_sc()[2 * lane] = s; s_sc()[2 * lane + 1] = c;
       }
@@ -249,13 +262,12 @@ struct WarpSolver {
         s_xp()[0] = R(0); s_xp()[1] = R(0); s_xp()[2] = R(0);
       }
     GMR_END
-    for (int l = 1; l < mc.nlevel; l++) {
+    for (int l = 1; l < dm.nlevel; l++) {
       const int beg = mc.lvl_off[l], cnt = mc.lvl_off[l + 1] - beg;
       GMR_LANES
         for (int e = lane; e < cnt; e += 32) {
           const int b = mc.lvl_body[beg + e], p = mc.parent[b];
-          const R* qp = s_xq() + 4 * p;
-          R pq[4] = {qp[0], qp[1], qp[2], qp[3]};
+          R pq[4]; g_ld4(s_xq() + 4 * p, pq);
           R off[3]; q_rot(pq, mc.bpos + 3 * b, off);
           s_xp()[3 * b] = s_xp()[3 * p] + off[0]; s_xp()[3 * b + 1] = s_xp()[3 * p + 1] + off[1]; s_xp()[3 * b + 2] = s_xp()[3 * p + 2] + off[2];
           R q[4]; q_mul(pq, mc.bquat + 4 * b, q);
@@ -267,15 +279,15 @@ struct WarpSolver {
           }
           // first-order renormalisation (|q| is 1 up to rounding): q *= 1.5 - 0.5 |q|^2
           const R k = R(1.5) - R(0.5) * (q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-          s_xq()[4 * b] = q[0] * k; s_xq()[4 * b + 1] = q[1] * k; s_xq()[4 * b + 2] = q[2] * k; s_xq()[4 * b + 3] = q[3] * k;
+          R* o = s_xq() + 4 * b;
+          o[0] = q[0] * k; o[1] = q[1] * k; o[2] = q[2] * k; o[3] = q[3] * k;
         }
       GMR_END
     }
     GMR_LANES
-      if (lane < mc.nh) {
+      if (lane < dm.nh) {
         const int b = mc.hbody[lane];
-        const R* qb = s_xq() + 4 * b;
-        R q[4] = {qb[0], qb[1], qb[2], qb[3]};
+        R q[4]; g_ld4(s_xq() + 4 * b, q);
         R w[3]; q_rot(q, mc.axis + 3 * lane, w);
         const R* d = s_xp() + 3 * b;
         R* o = s_sd() + 8 * lane;
@@ -287,23 +299,24 @@ struct WarpSolver {
   }
 
   // ------------------------------------------------------------------ targets (A1-A5) ------
-  // Raw keypoints of one frame (held per lane in L.in_pos/in_quat for lane < nhum) ->
+  // Raw keypoints of one frame (staged in s_in[h] = pos(3) pad quat(4), float) ->
   // scaled + offset targets in s_tg[h] = (pos[3], pad, quat[4]).
   GMR_FN void update_targets(R ratio, bool to_ground) {
     GMR_LANES
-      if (lane == mc.hroot) { s_red()[0] = R(L.in_pos[0]); s_red()[1] = R(L.in_pos[1]); s_red()[2] = R(L.in_pos[2]); }
+      if (lane == dm.hroot) { const float* in = s_in() + 8 * lane; s_red()[0] = R(in[0]); s_red()[1] = R(in[1]); s_red()[2] = R(in[2]); }
     GMR_END
     GMR_LANES
-      if (lane < mc.nhum) {
+      if (lane < dm.nhum) {
         const R rx = s_red()[0], ry = s_red()[1], rz = s_red()[2];
-        const R sr = mc.hscale[mc.hroot] * ratio;
+        const float* in = s_in() + 8 * lane;
+        const R sr = mc.hscale[dm.hroot] * ratio;
         R p[3];
-        if (lane == mc.hroot) { p[0] = sr * rx; p[1] = sr * ry; p[2] = sr * rz; }
+        if (lane == dm.hroot) { p[0] = sr * rx; p[1] = sr * ry; p[2] = sr * rz; }
         else {
           const R s = mc.hscale[lane] * ratio;
-          p[0] = (R(L.in_pos[0]) - rx) * s + sr * rx; p[1] = (R(L.in_pos[1]) - ry) * s + sr * ry; p[2] = (R(L.in_pos[2]) - rz) * s + sr * rz;
+          p[0] = (R(in[0]) - rx) * s + sr * rx; p[1] = (R(in[1]) - ry) * s + sr * ry; p[2] = (R(in[2]) - rz) * s + sr * rz;
         }
-        R q[4] = {R(L.in_quat[0]), R(L.in_quat[1]), R(L.in_quat[2]), R(L.in_quat[3])};
+        R q[4] = {R(in[4]), R(in[5]), R(in[6]), R(in[7])};
         R n = R(1) / g_sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
         q[0] *= n; q[1] *= n; q[2] *= n; q[3] *= n;
         R u[4]; q_mul(q, mc.hroff + 4 * lane, u);
@@ -317,134 +330,116 @@ struct WarpSolver {
     GMR_END
     if (to_ground) {      // offset_human_data_to_ground, motion_retarget.py:252-270
       R lowest = R(INFINITY);
-      for (int h = 0; h < mc.nhum; h++) if ((mc.foot_mask >> h) & 1u) { R z = s_tg()[8 * h + 2]; if (z < lowest) lowest = z; }
-#ifndef GMR_EMULATE
-      __syncwarp();
-#endif
+      for (int h = 0; h < dm.nhum; h++) if ((dm.foot_mask >> h) & 1u) { R z = s_tg()[8 * h + 2]; if (z < lowest) lowest = z; }
+      GMR_SYNC();
       GMR_LANES
-        if (lane < mc.nhum) s_tg()[8 * lane + 2] = s_tg()[8 * lane + 2] - lowest + R(0.1);
+        if (lane < dm.nhum) s_tg()[8 * lane + 2] = s_tg()[8 * lane + 2] - lowest + R(0.1);
       GMR_END
     }
   }
 
-  // ------------------------------------------------------------------ task kinematics (A7, A9)
-  // Per task: error e = log(T_b^-1 T_t) = (rho, omega); P = Jinv(omega) R_b^T;
-  // K' = -Jinv Q Jinv R_b^T - P [d_b]x  (the position rows' dependence on rotation, shifted to the
-  // root origin).  s_tk[t] = rho(3) omega(3) P(9) K'(9); s_red[t] = |e|^2.
-  GMR_FN void task_kinematics() {
+  // ------------------------------------------------------------------ tasks (A7, A9, A10) ---
+  // Per task: error e = log(T_b^-1 T_t) = (rho, omega) -> s_red[t] = |e|^2 (unweighted, all
+  // tasks); P = Jinv(omega) R_b^T;  K' = -Jinv Q Jinv R_b^T - P [d_b]x (the position rows'
+  // dependence on rotation, shifted to the root origin); then with the stage's weights
+  // s_mt[t] = M_t packed upper (21) | g_t (6) | mu_t, where
+  //   M = [[wp2 P^T P, wp2 P^T K'], [., wp2 K'^T K' + wr2 P^T P]],
+  //   g = A'^T W e = -[wp2 P^T rho ; wp2 K'^T rho + wr2 P^T omega],  mu = lm (wp2 |rho|^2 + wr2 |omega|^2).
+  GMR_FN void task_eval(int stage) {
+    const uint32_t stage_mask = stage == 0 ? dm.in1_mask : dm.in2_mask;
     GMR_LANES
-      if (lane < mc.nt) {
+      if (lane < dm.nt) {
         const int b = mc.tbody[lane], h = mc.thuman[lane];
-        const R* sq = s_xq() + 4 * b; const R* sd = s_xp() + 3 * b; const R* tg = s_tg() + 8 * h;
-        R qb[4] = {sq[0], sq[1], sq[2], sq[3]};
-        R d[3] = {sd[0], sd[1], sd[2]};
-        R qi[4] = {qb[0], -qb[1], -qb[2], -qb[3]};
-        R qt[4] = {tg[4], tg[5], tg[6], tg[7]};
-        R qe[4]; q_mul(qi, qt, qe);
-        if (qe[0] < R(0)) { qe[0] = -qe[0]; qe[1] = -qe[1]; qe[2] = -qe[2]; qe[3] = -qe[3]; }
-        // world offset target - body, via root-relative coordinates
-        R dw[3] = {(tg[0] - s_q()[0]) - d[0], (tg[1] - s_q()[1]) - d[1], (tg[2] - s_q()[2]) - d[2]};
-        R tb[3]; q_rot_inv(qb, dw, tb);
-        // SO(3) log
-        const R nsq = qe[1] * qe[1] + qe[2] * qe[2] + qe[3] * qe[3];
-        R fac, cV, th2;
-        R om[3];
-        const bool small = nsq < GmrEps<R>::lie;
-        if (small) {
-          fac = R(2) / qe[0] - R(2) / R(3) * nsq / (qe[0] * qe[0] * qe[0]);
-        } else {
-          const R n = g_sqrt(nsq);
-          fac = R(2) * g_atan2(n, qe[0]) / n;
-        }
-        om[0] = fac * qe[1]; om[1] = fac * qe[2]; om[2] = fac * qe[3];
-        th2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
-        // Jinv = I - S/2 + cV S^2 with cV = (1 - (theta/2) cot(theta/2)) / theta^2 (also V^-1 of SE3.log)
-        R Bq, Cq, Dq;   // Barfoot's Q coefficients
-        if (th2 < GmrEps<R>::lie) {
-          cV = R(1) / R(12);
-          Bq = R(1) / R(6); Cq = -R(1) / R(24); Dq = R(1) / R(120);
-        } else {
-          const R th = g_sqrt(th2);
-          const R n = g_sqrt(nsq);                       // sin(theta/2); qe[0] = cos(theta/2)
-          cV = (R(1) - R(0.5) * th * qe[0] / n) / th2;
-          if (th < R(0.25)) {                            // series: closed forms cancel badly for small theta
-            Bq = R(1) / R(6) - th2 * (R(1) / R(120) - th2 * (R(1) / R(5040) - th2 / R(362880)));
-            Cq = -R(1) / R(24) + th2 * (R(1) / R(720) - th2 * (R(1) / R(40320) - th2 / R(3628800)));
-            Dq = R(1) / R(120) - th2 * (R(1) / R(2520) - th2 * (R(1) / R(120960) - th2 / R(9979200)));
+        const R* tg = s_tg() + 8 * h;
+        R qb[4]; g_ld4(s_xq() + 4 * b, qb);
+        R d[3] = {s_xp()[3 * b], s_xp()[3 * b + 1], s_xp()[3 * b + 2]};
+        R rho[3], om[3], P[9], K[9];
+        R th2;
+        {
+          R qi[4] = {qb[0], -qb[1], -qb[2], -qb[3]};
+          R qt[4]; g_ld4(tg + 4, qt);
+          R qe[4]; q_mul(qi, qt, qe);
+          if (qe[0] < R(0)) { qe[0] = -qe[0]; qe[1] = -qe[1]; qe[2] = -qe[2]; qe[3] = -qe[3]; }
+          // world offset target - body, via root-relative coordinates
+          R dw[3] = {(tg[0] - s_q()[0]) - d[0], (tg[1] - s_q()[1]) - d[1], (tg[2] - s_q()[2]) - d[2]};
+          R tb[3]; q_rot_inv(qb, dw, tb);
+          // SO(3) log
+          const R nsq = qe[1] * qe[1] + qe[2] * qe[2] + qe[3] * qe[3];
+          R fac;
+          if (nsq < GmrEps<R>::lie) fac = R(2) / qe[0] - R(2) / R(3) * nsq / (qe[0] * qe[0] * qe[0]);
+          else { const R n = g_sqrt(nsq); fac = R(2) * g_atan2(n, qe[0]) / n; }
+          om[0] = fac * qe[1]; om[1] = fac * qe[2]; om[2] = fac * qe[3];
+          th2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
+          // Jinv = I - S/2 + cV S^2, cV = (1 - (theta/2) cot(theta/2)) / theta^2 (also V^-1 of SE3.log);
+          // Bq, Cq, Dq: Barfoot's Q coefficients
+          R cV, Bq, Cq, Dq;
+          if (th2 < GmrEps<R>::lie) {
+            cV = R(1) / R(12); Bq = R(1) / R(6); Cq = -R(1) / R(24); Dq = R(1) / R(120);
           } else {
-            const R st = R(2) * n * qe[0], ct = qe[0] * qe[0] - nsq;
-            Bq = (th - st) / (th2 * th);
-            Cq = (R(1) - th2 * R(0.5) - ct) / (th2 * th2);
-            Dq = (R(2) * th - R(3) * st + th * ct) / (R(2) * th2 * th2 * th);
+            const R th = g_sqrt(th2);
+            const R n = g_sqrt(nsq);                       // sin(theta/2); qe[0] = cos(theta/2)
+            cV = (R(1) - R(0.5) * th * qe[0] / n) / th2;
+            if (th < R(0.25)) {                            // series: the closed forms cancel badly for small theta
+              Bq = R(1) / R(6) - th2 * (R(1) / R(120) - th2 * (R(1) / R(5040) - th2 / R(362880)));
+              Cq = -R(1) / R(24) + th2 * (R(1) / R(720) - th2 * (R(1) / R(40320) - th2 / R(3628800)));
+              Dq = R(1) / R(120) - th2 * (R(1) / R(2520) - th2 * (R(1) / R(120960) - th2 / R(9979200)));
+            } else {
+              const R st = R(2) * n * qe[0], ct = qe[0] * qe[0] - nsq;
+              Bq = (th - st) / (th2 * th);
+              Cq = (R(1) - th2 * R(0.5) - ct) / (th2 * th2);
+              Dq = (R(2) * th - R(3) * st + th * ct) / (R(2) * th2 * th2 * th);
+            }
           }
-        }
-        R S[9], S2[9], Ji[9];
-        m3_skew(om, S); m3_mul(S, S, S2);
-        GMR_UNROLL
-        for (int i = 0; i < 9; i++) Ji[i] = ((i & 3) == 0 ? R(1) : R(0)) - R(0.5) * S[i] + cV * S2[i];
-        R rho[3] = {Ji[0] * tb[0] + Ji[1] * tb[1] + Ji[2] * tb[2], Ji[3] * tb[0] + Ji[4] * tb[1] + Ji[5] * tb[2], Ji[6] * tb[0] + Ji[7] * tb[1] + Ji[8] * tb[2]};
-        // Q(rho, omega) with W V W = -(omega.rho) W,  W V W W + W W V W = -2 (omega.rho) W^2
-        R V[9], VW[9], VWW[9], Q[9];
-        m3_skew(rho, V); m3_mul(V, S, VW); m3_mul(VW, S, VWW);
-        const R wr = om[0] * rho[0] + om[1] * rho[1] + om[2] * rho[2];
-        GMR_UNROLL
-        for (int i = 0; i < 3; i++) {
+          R S[9], S2[9], Ji[9];
+          m3_skew(om, S); m3_mul(S, S, S2);
           GMR_UNROLL
-          for (int j = 0; j < 3; j++) {
-            const int ij = 3 * i + j, ji = 3 * j + i;
-            const R wvw = -wr * S[ij];
-            Q[ij] = R(0.5) * V[ij] + Bq * (VW[ji] + VW[ij] + wvw) - Cq * (VWW[ij] - VWW[ji] - R(3) * wvw) + Dq * (-R(2) * wr * S2[ij]);
+          for (int i = 0; i < 9; i++) Ji[i] = ((i & 3) == 0 ? R(1) : R(0)) - R(0.5) * S[i] + cV * S2[i];
+          rho[0] = Ji[0] * tb[0] + Ji[1] * tb[1] + Ji[2] * tb[2];
+          rho[1] = Ji[3] * tb[0] + Ji[4] * tb[1] + Ji[5] * tb[2];
+          rho[2] = Ji[6] * tb[0] + Ji[7] * tb[1] + Ji[8] * tb[2];
+          // Q(rho, omega) with W V W = -(omega.rho) W,  W V W W + W W V W = -2 (omega.rho) W^2
+          R Q[9];
+          {
+            R V[9], VW[9], VWW[9];
+            m3_skew(rho, V); m3_mul(V, S, VW); m3_mul(VW, S, VWW);
+            const R wr = om[0] * rho[0] + om[1] * rho[1] + om[2] * rho[2];
+            GMR_UNROLL
+            for (int i = 0; i < 3; i++) {
+              GMR_UNROLL
+              for (int j = 0; j < 3; j++) {
+                const int ij = 3 * i + j, ji = 3 * j + i;
+                const R wvw = -wr * S[ij];
+                Q[ij] = R(0.5) * V[ij] + Bq * (VW[ji] + VW[ij] + wvw) - Cq * (VWW[ij] - VWW[ji] - R(3) * wvw) - Dq * R(2) * wr * S2[ij];
+              }
+            }
           }
+          R Rb[9]; q_to_mat(qb, Rb);
+          m3_mul_bt(Ji, Rb, P);                 // P = Jinv R_b^T
+          R T1[9], T2[9];
+          m3_mul(Ji, Q, T1); m3_mul(T1, P, T2); // Jinv Q Jinv R_b^T
+          R Sd[9], PS[9]; m3_skew(d, Sd); m3_mul(P, Sd, PS);
+          GMR_UNROLL
+          for (int i = 0; i < 9; i++) K[i] = -T2[i] - PS[i];
         }
-        R Rb[9]; q_to_mat(qb, Rb);
-        R P[9], T1[9], T2[9], K[9];
-        m3_mul_bt(Ji, Rb, P);                 // P = Jinv R_b^T
-        m3_mul(Ji, Q, T1); m3_mul(T1, P, T2); // Jinv Q Jinv R_b^T
-        R Sd[9], PS[9]; m3_skew(d, Sd); m3_mul(P, Sd, PS);
-        GMR_UNROLL
-        for (int i = 0; i < 9; i++) K[i] = -T2[i] - PS[i];
-        R* o = s_tk() + 24 * lane;
-        o[0] = rho[0]; o[1] = rho[1]; o[2] = rho[2]; o[3] = om[0]; o[4] = om[1]; o[5] = om[2];
-        GMR_UNROLL
-        for (int i = 0; i < 9; i++) { o[6 + i] = P[i]; o[15 + i] = K[i]; }
-        s_red()[lane] = rho[0] * rho[0] + rho[1] * rho[1] + rho[2] * rho[2] + th2;
-      }
-    GMR_END
-  }
-
-  // unweighted error norm of the stage's tasks (error1()/error2(), motion_retarget.py:188-200)
-  GMR_FN R stage_error(uint32_t stage_mask) const {
-    R s = R(0);
-    for (int t = 0; t < mc.nt; t++) if ((stage_mask >> t) & 1u) s += s_red()[t];
-    return g_sqrt(s);
-  }
-
-  // ------------------------------------------------------------------ task inertias (A9, A10)
-  // s_mt[t] = M_t packed upper (21) | g_t (6) | mu_t, for the stage's weights.
-  GMR_FN void task_inertias(const R* wtab, uint32_t stage_mask) {
-    GMR_LANES
-      if (lane < mc.nt) {
+        const R r2 = rho[0] * rho[0] + rho[1] * rho[1] + rho[2] * rho[2];
+        s_red()[lane] = r2 + th2;
         R* o = s_mt() + 28 * lane;
         const bool on = (stage_mask >> lane) & 1u;
+        const R* wtab = stage == 0 ? mc.w1 : mc.w2;
         const R wp = on ? wtab[2 * lane] : R(0), wr = on ? wtab[2 * lane + 1] : R(0);
         const R wp2 = wp * wp, wr2 = wr * wr;
-        const R* k = s_tk() + 24 * lane;
-        R rho[3] = {k[0], k[1], k[2]}, om[3] = {k[3], k[4], k[5]};
-        R P[9], K[9];
-        GMR_UNROLL
-        for (int i = 0; i < 9; i++) { P[i] = k[6 + i]; K[i] = k[15 + i]; }
-        R PtP[9], PtK[9], KtK[9];
-        m3_mul_at(P, P, PtP); m3_mul_at(P, K, PtK); m3_mul_at(K, K, KtK);
-        // M = [[wp2 PtP, wp2 PtK],[., wp2 KtK + wr2 PtP]]
-        GMR_UNROLL
-        for (int i = 0; i < 3; i++) {
+        {
+          R PtP[9], PtK[9], KtK[9];
+          m3_mul_at(P, P, PtP); m3_mul_at(P, K, PtK); m3_mul_at(K, K, KtK);
           GMR_UNROLL
-          for (int j = 0; j < 3; j++) {
-            if (j >= i) { o[gmr_sym6(i, j)] = wp2 * PtP[3 * i + j]; o[gmr_sym6(3 + i, 3 + j)] = wp2 * KtK[3 * i + j] + wr2 * PtP[3 * i + j]; }
-            o[gmr_sym6(i, 3 + j)] = wp2 * PtK[3 * i + j];
+          for (int i = 0; i < 3; i++) {
+            GMR_UNROLL
+            for (int j = 0; j < 3; j++) {
+              if (j >= i) { o[gmr_sym6(i, j)] = wp2 * PtP[3 * i + j]; o[gmr_sym6(3 + i, 3 + j)] = wp2 * KtK[3 * i + j] + wr2 * PtP[3 * i + j]; }
+              o[gmr_sym6(i, 3 + j)] = wp2 * PtK[3 * i + j];
+            }
           }
         }
-        // g = A'^T W e = -[wp2 P^T rho ; wp2 K^T rho + wr2 P^T om]
         GMR_UNROLL
         for (int i = 0; i < 3; i++) {
           const R ptr = P[i] * rho[0] + P[3 + i] * rho[1] + P[6 + i] * rho[2];
@@ -453,46 +448,63 @@ struct WarpSolver {
           o[21 + i] = -(wp2 * ptr);
           o[24 + i] = -(wp2 * ktr + wr2 * pto);
         }
-        o[27] = mc.lm * (wp2 * (rho[0] * rho[0] + rho[1] * rho[1] + rho[2] * rho[2]) + wr2 * (om[0] * om[0] + om[1] * om[1] + om[2] * om[2]));
+        o[27] = ks.lm * (wp2 * r2 + wr2 * th2);
       }
     GMR_END
-    // whole-tree composite for the floating base: s_root[0..20] = sum M, [21..26] = sum g, [27] = sum mu
+  }
+
+  // unweighted error norm of the stage's tasks (error1()/error2(), motion_retarget.py:188-200)
+  GMR_FN R stage_error(int stage) const {
+    const uint32_t m = stage == 0 ? dm.in1_mask : dm.in2_mask;
+    R s = R(0);
+    for (int t = 0; t < dm.nt; t++) if ((m >> t) & 1u) s += s_red()[t];
+    return g_sqrt(s);
+  }
+
+  // ------------------------------------------------------------------ composites ------------
+  // whole-tree composite for the floating base, per-hinge composite -> f_i = Ic_i s_i,
+  // c_i = s_i . G_i, diag_i = s_i . f_i + damping + sum mu
+  GMR_FN void composites() {
     GMR_LANES
       if (lane < 28) {
         R s = R(0);
-        for (int t = 0; t < mc.nt; t++) s += s_mt()[28 * t + lane];
+        for (int t = 0; t < dm.nt; t++) s += s_mt()[28 * t + lane];
         s_root()[lane] = s;
       }
     GMR_END
-    // per-hinge composite -> f_i = Ic_i s_i, c_i = s_i . G_i, diag
     GMR_LANES
-      if (lane < mc.nh) {
-        R acc[27];
+      if (lane < dm.nh) {
+        R acc[28];
         GMR_UNROLL
-        for (int i = 0; i < 27; i++) acc[i] = R(0);
+        for (int i = 0; i < 28; i++) acc[i] = R(0);
         const uint32_t tm = mc.task_mask[lane];
-        for (int t = 0; t < mc.nt; t++) {
+        for (int t = 0; t < dm.nt; t++) {
           if ((tm >> t) & 1u) {
             const R* m = s_mt() + 28 * t;
             GMR_UNROLL
-            for (int i = 0; i < 27; i++) acc[i] += m[i];
+            for (int c = 0; c < 7; c++) {
+              R v[4]; g_ld4(m + 4 * c, v);
+              acc[4 * c] += v[0]; acc[4 * c + 1] += v[1]; acc[4 * c + 2] += v[2]; acc[4 * c + 3] += v[3];
+            }
           }
         }
-        const R* s = s_sd() + 8 * lane;
-        R sv[6] = {s[0], s[1], s[2], s[3], s[4], s[5]};
+        R sv[8]; g_ld4(s_sd() + 8 * lane, sv); g_ld4(s_sd() + 8 * lane + 4, sv + 4);
         R dg = R(0), ci = R(0);
         GMR_UNROLL
         for (int i = 0; i < 6; i++) {
           R v = R(0);
           GMR_UNROLL
           for (int j = 0; j < 6; j++) v += acc[gmr_sym6(i, j)] * sv[j];
-          L.f[i] = v; dg += v * sv[i]; ci += acc[21 + i] * sv[i];
+          lp(LP_F + i, lane) = v; dg += v * sv[i]; ci += acc[21 + i] * sv[i];
         }
-        L.diag = dg + mc.damping + s_root()[27];
-        L.ci = ci;
+        lp(LP_DIAG, lane) = dg + ks.damping + s_root()[27];
+        lp(LP_CI, lane) = ci;
       }
     GMR_END
   }
+
+  GMR_FN R bound_hi(int j) const { return ((dm.limited_mask >> j) & 1u) ? ks.gain * (mc.hi[j] - s_q()[7 + j]) : R(INFINITY); }
+  GMR_FN R bound_lo(int j) const { return ((dm.limited_mask >> j) & 1u) ? -(ks.gain * (s_q()[7 + j] - mc.lo[j])) : -R(INFINITY); }
 
   // ------------------------------------------------------------------ rows of H -------------
   // lane i: row[j] = f_i . s_j for hinge ancestors j, row[i] = diag, a[] = f_i (base columns are
@@ -500,28 +512,29 @@ struct WarpSolver {
   // identity rows with rhs = bound, free lanes move the pinned columns to the right-hand side.
   GMR_FN void build_rows(uint32_t pinned) {
     GMR_LANES
-      if (lane < mc.nh) {
+      if (lane < dm.nh) {
         const uint32_t am = mc.anc_mask[lane];
+        const R f0 = lp(LP_F, lane), f1 = lp(LP_F + 1, lane), f2 = lp(LP_F + 2, lane), f3 = lp(LP_F + 3, lane), f4 = lp(LP_F + 4, lane), f5 = lp(LP_F + 5, lane);
+        const R dg = lp(LP_DIAG, lane);
         GMR_UNROLL
         for (int j = 0; j < GMR_NH; j++) {
           R v = R(0);
-          if (j < mc.nh && ((am >> j) & 1u)) {
-            const R* s = s_sd() + 8 * j;
-            v = L.f[0] * s[0] + L.f[1] * s[1] + L.f[2] * s[2] + L.f[3] * s[3] + L.f[4] * s[4] + L.f[5] * s[5];
+          if (j < dm.nh && ((am >> j) & 1u)) {
+            R s[8]; g_ld4(s_sd() + 8 * j, s); g_ld4(s_sd() + 8 * j + 4, s + 4);
+            v = f0 * s[0] + f1 * s[1] + f2 * s[2] + f3 * s[3] + f4 * s[4] + f5 * s[5];
           }
-          L.row[j] = (j == lane) ? L.diag : v;
+          L.row[j] = (j == lane) ? dg : v;
         }
-        GMR_UNROLL
-        for (int g = 0; g < 6; g++) L.a[g] = L.f[g];
-        L.rhs = -L.ci;
+        L.a[0] = f0; L.a[1] = f1; L.a[2] = f2; L.a[3] = f3; L.a[4] = f4; L.a[5] = f5;
+        L.rhs = -lp(LP_CI, lane);
       }
     GMR_END
     if (pinned) {
       // pinned lanes publish (their column of H) * bound; s_bnd holds the bound values
       GMR_LANES
-        if (lane < mc.nh && ((pinned >> lane) & 1u)) {
+        if (lane < dm.nh && ((pinned >> lane) & 1u)) {
           const R bv = s_bnd()[lane];
-          R* o = s_L() + gmr_loff_rt(lane);
+          R* o = s_L() + gmr_loff(lane);
           GMR_UNROLL
           for (int g = 0; g < 6; g++) o[g] = L.a[g] * bv;
           GMR_UNROLL
@@ -529,7 +542,7 @@ struct WarpSolver {
         }
       GMR_END
       GMR_LANES
-        if (lane < mc.nh) {
+        if (lane < dm.nh) {
           if ((pinned >> lane) & 1u) {
             GMR_UNROLL
             for (int g = 0; g < 6; g++) L.a[g] = R(0);
@@ -542,37 +555,30 @@ struct WarpSolver {
             for (int j = 0; j < GMR_NH; j++) {
               if ((pinned >> j) & 1u) {
                 if (j < lane) { r -= L.row[j] * s_bnd()[j]; L.row[j] = R(0); }
-                else if (j > lane && j < mc.nh) r -= s_L()[gmr_loff_rt(j) + 6 + lane];
+                else if (j > lane && j < dm.nh) r -= s_L()[gmr_loff(j) + 6 + lane];
               }
             }
             L.rhs = r;
           }
         }
-        // base right-hand side correction, gathered by lanes 0..5 into s_piv-free scratch s_xs[0..5]
+        // base right-hand side correction, gathered by lanes 0..5 into s_xs[0..5]
         if (lane < 6) {
           R r = R(0);
-          for (int j = 0; j < mc.nh; j++) if ((pinned >> j) & 1u) r += s_L()[gmr_loff_rt(j) + lane];
+          for (int j = 0; j < dm.nh; j++) if ((pinned >> j) & 1u) r += s_L()[gmr_loff(j) + lane];
           s_xs()[lane] = r;
         }
       GMR_END
     }
   }
 
-  GMR_FN static int gmr_loff_rt(int k) {      // runtime version of gmr_loff
-    // sum_{i<k} pad4(6+i): rows come in groups of four equal lengths after the first two
-    int o = 0;
-    for (int i = 0; i < k; i++) o += (6 + i + 3) & ~3;
-    return o;
-  }
-
   // ------------------------------------------------------------------ factor + solve --------
-  // Solves H x = rhs for the rows built above; result in s_xs[0..nv) (base first) and L.xs.
+  // Solves H x = rhs for the rows built above; result in s_xs[0..nv) (base first).
   GMR_FN void factor_solve(uint32_t pinned) {
-    // 6x6 base block, factored redundantly by every lane (uniform data from s_root)
+    // 6x6 base block (uniform data from s_root), factored by lane 0
     GMR_LANES
       if (lane == 0) {
         const R* c = s_root();
-        const R dd = mc.damping + c[27];
+        const R dd = ks.damping + c[27];
         R A[21];
         GMR_UNROLL
         for (int i = 0; i < 21; i++) A[i] = c[i];
@@ -614,8 +620,10 @@ struct WarpSolver {
     GMR_END
     // every hinge row: a' = a Lf^-T (forward substitution on its own 6 values), rhs -= a'.yf
     GMR_LANES
-      if (lane < mc.nh) {
-        const R* lf = s_lf();
+      if (lane < dm.nh) {
+        R lf[28];
+        GMR_UNROLL
+        for (int c = 0; c < 7; c++) g_ld4(s_lf() + 4 * c, lf + 4 * c);
         R r = L.rhs;
         GMR_UNROLL
         for (int i = 0; i < 6; i++) {
@@ -627,26 +635,33 @@ struct WarpSolver {
           r -= s * lf[21 + i];
         }
         L.rhs = r;
-        R* o = s_L() + gmr_loff_rt(lane);
+        R* o = s_L() + gmr_loff(lane);
         GMR_UNROLL
         for (int g = 0; g < 6; g++) o[g] = L.a[g];
       }
     GMR_END
-    // hinge block, column by column (pivot k unrolled so that row[] stays in registers)
+    // hinge block, column by column (pivot k unrolled so that row[] stays in registers);
+    // the pivot row (6 base + k hinge entries) is broadcast from shared memory 4 values at a time
     GMR_UNROLL
     for (int k = 0; k < GMR_NH; k++) {
-      if (k < mc.nh) {
+      if (k < dm.nh) {
         GMR_LANES
-          if (lane >= k && lane < mc.nh) {
+          if (lane >= k && lane < dm.nh) {
             const R* lk = s_L() + gmr_loff(k);
             R s = L.row[k];
             GMR_UNROLL
-            for (int g = 0; g < 6; g++) s -= L.a[g] * lk[g];
-            GMR_UNROLL
-            for (int m = 0; m < k; m++) s -= L.row[m] * lk[6 + m];
+            for (int c = 0; c < (6 + k + 3) / 4; c++) {
+              R v[4]; g_ld4(lk + 4 * c, v);
+              GMR_UNROLL
+              for (int e = 0; e < 4; e++) {
+                const int i = 4 * c + e;
+                if (i < 6) s -= L.a[i < 6 ? i : 0] * v[e];
+                else if (i < 6 + k) s -= L.row[(i >= 6 && i < 6 + GMR_NH) ? i - 6 : 0] * v[e];
+              }
+            }
             if (lane == k) {
               const R d = g_sqrt(s), di = R(1) / d;
-              L.row[k] = d; L.dinv = di;
+              L.dinv = di;
               const R y = L.rhs * di;
               L.rhs = y;
               s_piv()[0] = di; s_piv()[1] = y;
@@ -656,10 +671,10 @@ struct WarpSolver {
           }
         GMR_END
         GMR_LANES
-          if (lane > k && lane < mc.nh) {
+          if (lane > k && lane < dm.nh) {
             const R l = L.tmp * s_piv()[0];
             L.row[k] = l;
-            s_L()[gmr_loff_rt(lane) + 6 + k] = l;
+            s_L()[gmr_loff(lane) + 6 + k] = l;
             L.rhs -= l * s_piv()[1];
           }
         GMR_END
@@ -672,9 +687,9 @@ struct WarpSolver {
     GMR_UNROLL
     for (int kk = 0; kk < GMR_NH; kk++) {
       const int k = GMR_NH - 1 - kk;
-      if (k < mc.nh) {
+      if (k < dm.nh) {
         GMR_LANES
-          if (lane == k) { const R x = L.rhs * L.dinv; L.xs = x; s_xs()[6 + k] = x; }
+          if (lane == k) s_xs()[6 + k] = L.rhs * L.dinv;
         GMR_END
         GMR_LANES
           const R x = s_xs()[6 + k];
@@ -708,124 +723,124 @@ struct WarpSolver {
   }
 
   // ------------------------------------------------------------------ box QP (A10, A11) -----
-  // min 1/2 x^T H x + c^T x, lo <= x_hinge <= hi: primal active set from clip(0, lo, hi).
-  // Returns the number of factorisations; the step is left in s_xs[0..nv).
-  GMR_FN int solve_qp() {
+  // min 1/2 x^T H x + c^T x, lo <= x_hinge <= hi: primal active set from a feasible start.
+  // The step is left in s_xs[0..nv).  One code instance of build_rows/factor_solve: the loop
+  // alternates between SOLVE passes and (only when bounds are pinned) a CHECK pass that
+  // evaluates the KKT multipliers on the original rows.
+  GMR_FN void solve_qp() {
     const R INF = R(INFINITY);
     GMR_LANES
-      if (lane < mc.nh) {
-        if ((mc.limited_mask >> lane) & 1u) {
-          const R qj = s_q()[7 + lane];
-          L.bhi = mc.gain * (mc.hi[lane] - qj);
-          L.blo = -(mc.gain * (qj - mc.lo[lane]));
-        } else { L.bhi = INF; L.blo = -INF; }
+      if (lane < dm.nh) {
         // feasible start: bounds that were active at the end of the previous solve stay in the
         // working set (their joints sit on, or creep towards, the limit), everything else at
         // clip(0, lo, hi).  Any feasible start gives the same (unique) optimum.
-        if ((warm_hi >> lane) & 1u) L.x = L.bhi;
-        else if ((warm_lo >> lane) & 1u) L.x = L.blo;
-        else L.x = R(0) < L.blo ? L.blo : (R(0) > L.bhi ? L.bhi : R(0));
+        const R bhi = bound_hi(lane), blo = bound_lo(lane);
+        R x;
+        if ((warm_hi >> lane) & 1u) x = bhi;
+        else if ((warm_lo >> lane) & 1u) x = blo;
+        else x = R(0) < blo ? blo : (R(0) > bhi ? bhi : R(0));
+        lp(LP_X, lane) = x;
       }
     GMR_END
-    uint32_t pin_lo = warm_lo & mc.limited_mask, pin_hi = warm_hi & mc.limited_mask;
-    int nfac = 0;
-    const int max_as = 4 * mc.nh + 8;
+    uint32_t pin_lo = warm_lo & dm.limited_mask, pin_hi = warm_hi & dm.limited_mask;
+    bool check = false;
+    const int max_as = 8 * dm.nh + 16;
     for (int it = 0; it < max_as; it++) {
       const uint32_t pinned = pin_lo | pin_hi;
-      if (pinned) {
+      if (!check && pinned) {
         GMR_LANES
-          if (lane < mc.nh) s_bnd()[lane] = ((pin_hi >> lane) & 1u) ? L.bhi : L.blo;
+          if (lane < dm.nh) s_bnd()[lane] = ((pin_hi >> lane) & 1u) ? bound_hi(lane) : bound_lo(lane);
         GMR_END
       }
-      build_rows(pinned);
-      factor_solve(pinned);
-      nfac++;
-      // ratio test towards the candidate
-      GMR_LANES
-        if (lane < mc.nh) {
-          R al = INF;
-          if (!((pinned >> lane) & 1u)) {
-            const R p = L.xs - L.x;
-            if (p > R(0) && L.bhi < INF) al = (L.bhi - L.x) / p;
-            else if (p < R(0) && L.blo > -INF) al = (L.blo - L.x) / p;
-          } else {
-            L.xs = L.x;                        // pinned: stays on its bound
-          }
-          s_red()[lane] = al;
-        }
-      GMR_END
-      R alpha = R(1); int blk = -1;
-      for (int j = 0; j < mc.nh; j++) { const R a = s_red()[j]; if (a < alpha) { alpha = a; blk = j; } }
-#ifndef GMR_EMULATE
-      __syncwarp();
-#endif
-      if (blk >= 0) {
-        if (alpha < R(0)) alpha = R(0);
-        int side = 0;
+      build_rows(check ? 0u : pinned);
+      if (!check) {
+        factor_solve(pinned);
+        stat_refactor++;
+        // ratio test towards the candidate
         GMR_LANES
-          if (lane < mc.nh) {
-            if (lane == blk) {
-              const bool up = (L.xs - L.x) > R(0);
-              L.x = up ? L.bhi : L.blo;
-              s_piv()[2] = up ? R(1) : R(-1);
-            } else if (!((pinned >> lane) & 1u)) {
-              L.x += alpha * (L.xs - L.x);
+          if (lane < dm.nh) {
+            R al = INF;
+            const R x = lp(LP_X, lane);
+            if (!((pinned >> lane) & 1u)) {
+              const R p = s_xs()[6 + lane] - x;
+              const R bhi = bound_hi(lane), blo = bound_lo(lane);
+              if (p > R(0) && bhi < INF) al = (bhi - x) / p;
+              else if (p < R(0) && blo > -INF) al = (blo - x) / p;
+            } else {
+              s_xs()[6 + lane] = x;                        // pinned: stays on its bound
             }
+            s_red()[lane] = al;
           }
         GMR_END
-        side = s_piv()[2] > R(0) ? 1 : -1;
-#ifndef GMR_EMULATE
-        __syncwarp();
-#endif
-        if (side > 0) pin_hi |= 1u << blk; else pin_lo |= 1u << blk;
+        R alpha = R(1); int blk = -1;
+        for (int j = 0; j < dm.nh; j++) { const R a = s_red()[j]; if (a < alpha) { alpha = a; blk = j; } }
+        GMR_SYNC();
+        if (blk >= 0) {
+          if (alpha < R(0)) alpha = R(0);
+          GMR_LANES
+            if (lane < dm.nh) {
+              const R x = lp(LP_X, lane), p = s_xs()[6 + lane] - x;
+              if (lane == blk) {
+                const bool up = p > R(0);
+                lp(LP_X, lane) = up ? bound_hi(lane) : bound_lo(lane);
+                s_piv()[2] = up ? R(1) : R(-1);
+              } else if (!((pinned >> lane) & 1u)) {
+                lp(LP_X, lane) = x + alpha * p;
+              }
+            }
+          GMR_END
+          const bool up = s_piv()[2] > R(0);
+          GMR_SYNC();
+          if (up) pin_hi |= 1u << blk; else pin_lo |= 1u << blk;
+          continue;
+        }
+        GMR_LANES
+          if (lane < dm.nh) lp(LP_X, lane) = s_xs()[6 + lane];
+        GMR_END
+        if (!pinned) break;
+        check = true;
         continue;
       }
+      // CHECK pass: g = H x + c on the original rows (just rebuilt); x is in s_xs
       GMR_LANES
-        if (lane < mc.nh) L.x = L.xs;
-      GMR_END
-      if (!pinned) break;
-      // KKT multipliers of the pinned bounds: g = H x + c on the ORIGINAL rows
-      build_rows(0);
-      GMR_LANES
-        if (lane < mc.nh) {
-          R* o = s_L() + gmr_loff_rt(lane);
+        if (lane < dm.nh) {
+          R* o = s_L() + gmr_loff(lane);
+          const R x = lp(LP_X, lane);
           GMR_UNROLL
-          for (int j = 0; j < GMR_NH; j++) if (j < lane) o[6 + j] = L.row[j] * L.x;
+          for (int j = 0; j < GMR_NH; j++) if (j < lane) o[6 + j] = L.row[j] * x;
         }
       GMR_END
       GMR_LANES
-        R lam = INF;
-        if (lane < mc.nh) {
+        if (lane < dm.nh) {
+          R lam = INF;
           if ((pinned >> lane) & 1u) {
-            R g = L.ci + L.diag * L.x;
+            R g = lp(LP_CI, lane) + lp(LP_DIAG, lane) * lp(LP_X, lane);
             GMR_UNROLL
             for (int f = 0; f < 6; f++) g += L.a[f] * s_xs()[f];
             GMR_UNROLL
             for (int j = 0; j < GMR_NH; j++) if (j < lane) g += L.row[j] * s_xs()[6 + j];
-            for (int i = lane + 1; i < mc.nh; i++) g += s_L()[gmr_loff_rt(i) + 6 + lane];
+            for (int i = lane + 1; i < dm.nh; i++) g += s_L()[gmr_loff(i) + 6 + lane];
             lam = ((pin_lo >> lane) & 1u) ? g : -g;
           }
           s_red()[lane] = lam;
         }
       GMR_END
       R lmin = R(0), gmax = R(1); int worst = -1;
-      for (int j = 0; j < mc.nh; j++) if ((pinned >> j) & 1u) {
+      for (int j = 0; j < dm.nh; j++) if ((pinned >> j) & 1u) {
         const R l = s_red()[j];
         if (g_abs(l) > gmax) gmax = g_abs(l);
         if (worst < 0 || l < lmin) { lmin = l; worst = j; }
       }
-#ifndef GMR_EMULATE
-      __syncwarp();
-#endif
+      GMR_SYNC();
       if (worst < 0 || lmin >= -GmrEps<R>::lam * gmax) break;
       pin_lo &= ~(1u << worst); pin_hi &= ~(1u << worst);
+      check = false;
     }
     warm_lo = pin_lo; warm_hi = pin_hi;
     // publish the final step (hinge part) for integration
     GMR_LANES
-      if (lane < mc.nh) s_xs()[6 + lane] = L.x;
+      if (lane < dm.nh) s_xs()[6 + lane] = lp(LP_X, lane);
     GMR_END
-    return nfac;
   }
 
   // ------------------------------------------------------------------ integration (A12) ------
@@ -834,15 +849,15 @@ struct WarpSolver {
   // rotated into the root frame first.
   GMR_FN void integrate() {
     GMR_LANES
-      const R dt = mc.dt;
-      if (lane < mc.nh) {
+      const R dt = ks.dt;
+      if (lane < dm.nh) {
         const R v = s_xs()[6 + lane] / dt;
         s_q()[7 + lane] += dt * v;
       }
       if (lane == 0) {
         GMR_UNROLL
         for (int i = 0; i < 3; i++) { const R v = s_xs()[i] / dt; s_q()[i] += dt * v; }
-        R q[4] = {s_xq()[0], s_xq()[1], s_xq()[2], s_xq()[3]};     // normalised root quaternion
+        R q[4]; g_ld4(s_xq(), q);                                  // normalised root quaternion
         R ww[3] = {s_xs()[3], s_xs()[4], s_xs()[5]}, wl[3];
         q_rot_inv(q, ww, wl);
         R v[3] = {wl[0] / dt, wl[1] / dt, wl[2] / dt};
@@ -863,75 +878,111 @@ struct WarpSolver {
     GMR_END
   }
 
-  // ------------------------------------------------------------------ one stage (A13) --------
-  // Assumes task_kinematics() is current.  Returns number of solves; *err = final stage error.
-  GMR_FN int run_stage(int stage, R* err) {
-    const uint32_t mask = stage == 0 ? mc.in1_mask : mc.in2_mask;
-    const R* wtab = stage == 0 ? mc.w1 : mc.w2;
-    R curr = stage_error(mask);
-    int nsolve = 0, num_iter = 0;
-    R next;
-    for (;;) {
-      task_inertias(wtab, mask);
-      stat_refactor += solve_qp();
-      integrate();
-      fk();
-      task_kinematics();
-      next = stage_error(mask);
-      nsolve++;
-      if (nsolve == 1) { if (!(curr - next > mc.tol && num_iter < mc.max_iter)) break; }
-      else { num_iter++; if (!(curr - next > mc.tol && num_iter < mc.max_iter)) break; }
-      curr = next;
-    }
-    *err = next;
-    return nsolve;
-  }
-  // ------------------------------------------------------------------ one clip ---------------
-  GMR_FN void load_frame(const float* pos, const float* quat) {
+  // ------------------------------------------------------------------ keypoint stream -------
+  // Asynchronous copy (cp.async, LDGSTS) of one frame's raw keypoints into the staging area;
+  // frame_wait() must be called before update_targets() reads them.
+  GMR_FN void stage_frame(const float* pos, const float* quat) {
     GMR_LANES
-      if (lane < mc.nhum) {
+      if (lane < dm.nhum) {
+        float* dst = s_in() + 8 * lane;
         const float* p = pos + 3 * lane;
-        L.in_pos[0] = p[0]; L.in_pos[1] = p[1]; L.in_pos[2] = p[2];
-#ifdef GMR_EMULATE
         const float* q = quat + 4 * lane;
-        L.in_quat[0] = q[0]; L.in_quat[1] = q[1]; L.in_quat[2] = q[2]; L.in_quat[3] = q[3];
+#ifdef GMR_EMULATE
+        dst[0] = p[0]; dst[1] = p[1]; dst[2] = p[2];
+        dst[4] = q[0]; dst[5] = q[1]; dst[6] = q[2]; dst[7] = q[3];
 #else
-        const float4 q = __ldg(reinterpret_cast<const float4*>(quat) + lane);
-        L.in_quat[0] = q.x; L.in_quat[1] = q.y; L.in_quat[2] = q.z; L.in_quat[3] = q.w;
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(p) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 4), "l"(p + 1) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 8), "l"(p + 2) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(q) : "memory");
 #endif
       }
+#ifndef GMR_EMULATE
+      asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
     GMR_END
   }
+  GMR_FN void frame_wait() {
+#ifndef GMR_EMULATE
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+#endif
+  }
 
+  // ------------------------------------------------------------------ one clip (A13) --------
   // pos/quat point at this clip's first frame ([T,nhum,3] / [T,nhum,4]); outputs at this clip's
-  // first frame too.  Null output pointers are skipped.
+  // first frame too.  Null output pointers are skipped.  The per-frame control flow of
+  // retarget() (motion_retarget.py:139-185) is flattened into one loop so that every phase
+  // exists once in the instruction stream:
+  //   per stage:  curr = err(); solve; next = err(); n = 0
+  //               while curr - next > tol and n < max_iter: curr = next; solve; next = err(); n += 1
   template <typename IO>
   GMR_FN void run_clip(const float* pos, const float* quat, R ratio, int T, const IO* qinit, IO* qpos_out,
                        int32_t* iters_out, IO* err_out, IO* tg_out, uint32_t flags) {
     if (qinit) set_qpos(qinit); else set_qpos(mc.qpos0);
     warm_lo = warm_hi = 0;
-    fk();
-    if (T > 0) load_frame(pos, quat);
-    for (int t = 0; t < T; t++) {
-      update_targets(ratio, (flags & GMR_FLAG_OFFSET_TO_GROUND) != 0);
-      if (t + 1 < T) load_frame(pos + (size_t)(t + 1) * mc.nhum * 3, quat + (size_t)(t + 1) * mc.nhum * 4);
-      task_kinematics();
-      int n1 = 0, n2 = 0; R e1 = R(0), e2 = R(0);
-      if (mc.use1) n1 = run_stage(0, &e1);
-      if (mc.use2) n2 = run_stage(1, &e2);
-      GMR_LANES
-        IO* qo = qpos_out + (size_t)t * mc.nq;
-        for (int i = lane; i < mc.nq; i += 32) qo[i] = IO(s_q()[i]);
-        if (lane == 0) {
-          if (iters_out) { iters_out[2 * t] = n1; iters_out[2 * t + 1] = n2; }
-          if (err_out) { err_out[2 * t] = IO(e1); err_out[2 * t + 1] = IO(e2); }
+    if (T <= 0) return;
+    stage_frame(pos, quat);
+    const int first_stage = dm.use1 ? 0 : 1;
+    const bool any_stage = dm.use1 || dm.use2;
+    int t = 0, stage = first_stage, nsolve = 0;
+    int n0 = 0, n1 = 0;
+    R e0 = R(0), e1 = R(0);
+    R curr = R(0);
+    bool frame_start = true, need_fk = true;
+    for (;;) {
+      if (frame_start) {
+        frame_wait();
+        update_targets(ratio, (flags & GMR_FLAG_OFFSET_TO_GROUND) != 0);
+        if (t + 1 < T) stage_frame(pos + (size_t)(t + 1) * dm.nhum * 3, quat + (size_t)(t + 1) * dm.nhum * 4);
+        stage = first_stage; nsolve = 0; n0 = n1 = 0; e0 = e1 = R(0);
+        frame_start = false;
+      }
+      if (need_fk) { fk(); need_fk = false; }
+      bool solve = false, done = !any_stage;
+      if (any_stage) {
+        task_eval(stage);
+        const R e = stage_error(stage);
+        if (flags & GMR_FLAG_NO_SOLVE) {                 // targets + errors only (update_targets / error1 / error2)
+          if (stage == 0) e0 = e; else e1 = e;
+          if (stage == 0 && dm.use2) { stage = 1; continue; }
+          done = true;
         }
-        if (tg_out && lane < mc.nhum) {
-          IO* o = tg_out + ((size_t)t * mc.nhum + lane) * 7;
-          const R* g = s_tg() + 8 * lane;
-          o[0] = IO(g[0]); o[1] = IO(g[1]); o[2] = IO(g[2]); o[3] = IO(g[4]); o[4] = IO(g[5]); o[5] = IO(g[6]); o[6] = IO(g[7]);
+        else if (nsolve == 0) { curr = e; solve = true; }
+        else if (curr - e > ks.tol && nsolve - 1 < dm.max_iter) { curr = e; solve = true; }
+        else {
+          if (stage == 0) { n0 = nsolve; e0 = e; } else { n1 = nsolve; e1 = e; }
+          if (stage == 0 && dm.use2) { stage = 1; nsolve = 0; continue; }   // re-evaluate with stage-2 weights
+          done = true;
         }
-      GMR_END
+      }
+      if (solve) {
+        composites();
+        solve_qp();
+        integrate();
+        need_fk = true;
+        nsolve++;
+        continue;
+      }
+      if (done) {
+        GMR_LANES
+          IO* qo = qpos_out + (size_t)t * dm.nq;
+          for (int i = lane; i < dm.nq; i += 32) qo[i] = IO(s_q()[i]);
+          if (lane == 0) {
+            if (iters_out) { iters_out[2 * t] = n0; iters_out[2 * t + 1] = n1; }
+            if (err_out) { err_out[2 * t] = IO(e0); err_out[2 * t + 1] = IO(e1); }
+          }
+          if (tg_out && lane < dm.nhum) {
+            IO* o = tg_out + ((size_t)t * dm.nhum + lane) * 7;
+            const R* g = s_tg() + 8 * lane;
+            o[0] = IO(g[0]); o[1] = IO(g[1]); o[2] = IO(g[2]); o[3] = IO(g[4]); o[4] = IO(g[5]); o[5] = IO(g[6]); o[6] = IO(g[7]);
+          }
+        GMR_END
+        t++;
+        if (t == T) break;
+        frame_start = true;
+      }
     }
   }
 };

@@ -1,0 +1,389 @@
+"""`GeneralMotionRetargeting` — drop-in for the reference class of the same name
+(reference general_motion_retargeting/motion_retarget.py:10-270) with the per-frame IK solve
+running in the sm_100a CUDA library (csrc/libgmr_b200.so) instead of mink/MuJoCo/DAQP.
+
+Kept from the reference: the constructor signature (:13-21), ``retarget(human_data,
+offset_to_ground=False) -> qpos[nq]`` float64 ``[x y z qw qx qy qz hinge…]`` (:139-185),
+``update_targets`` (:117-136), ``error1``/``error2`` (:188-200), the helper methods
+``to_numpy``/``scale_human_data``/``offset_human_data``/``offset_human_data_to_ground``
+(:203-270) and the public attributes callers read (``xml_file``, ``scaled_human_data``,
+``ik_match_table1/2``, ``human_scale_table``, ``max_iter`` …).
+
+Added: ``retarget_batch(pos, quat, heights)`` — C clips × T frames in one launch, clip ``c``
+being exactly ``GMR(src, robot, heights[c])`` followed by ``for t: retarget(frame[c, t])``;
+this is what scripts/smplx_to_robot_dataset.py:84-87 and scripts/bvh_to_robot_dataset.py:96-103
+call instead of their per-frame loop.
+
+There is no CPU fallback: constructing the class without the built CUDA library raises.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+import types
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _native
+from .ik_config import IKConfig, TaskTable, compile_task_table
+from .mjcf import RobotModel
+from .params import IK_CONFIG_DICT, ROBOT_XML_DICT, load_pack
+
+FLAG_OFFSET_TO_GROUND = 1
+FLAG_NO_SOLVE = 2
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.split(".")[0] == "torch"
+
+
+class _Handle:
+    """One gmr_model_create() handle per (instance, device)."""
+
+    def __init__(self, lib, desc, device: int):
+        self.lib = lib
+        self.ptr = C.c_void_p()
+        rc = lib.gmr_model_create(C.byref(desc), device, C.byref(self.ptr))
+        if rc != 0:
+            raise RuntimeError(f"gmr_model_create failed ({rc}): {lib.gmr_last_error().decode()}")
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.gmr_model_destroy(self.ptr)
+        except Exception:
+            pass
+
+
+class GeneralMotionRetargeting:
+    """General Motion Retargeting (GMR), B200-native solve."""
+
+    def __init__(
+        self,
+        src_human: str,
+        tgt_robot: str,
+        actual_human_height: Optional[float] = None,
+        solver: str = "daqp",
+        damping: float = 5e-1,
+        verbose: bool = False,
+        device: Union[int, str, None] = None,
+        precision: str = "f64",
+    ) -> None:
+        # the robot model and IK config (KeyError on unknown names, like the reference's dict lookups)
+        self.xml_file = str(ROBOT_XML_DICT[tgt_robot])
+        self._robot, cfg, _pack = load_pack(src_human, tgt_robot)
+        self._cfg: IKConfig = cfg
+        if verbose:
+            print("Use robot model: ", self.xml_file)
+            print("Use IK config: ", IK_CONFIG_DICT[src_human][tgt_robot])
+        if precision not in ("f32", "f64"):
+            raise ValueError("precision must be 'f32' or 'f64'")
+        self.precision = precision
+        self.src_human, self.tgt_robot = src_human, tgt_robot
+
+        # height ratio (motion_retarget.py:36-43)
+        if actual_human_height is not None:
+            ratio = actual_human_height / cfg.human_height_assumption
+        else:
+            ratio = 1.0
+        self._ratio = float(ratio)
+        self.human_scale_table = {k: v * ratio for k, v in cfg.human_scale_table.items()}
+
+        self.ik_match_table1 = copy.deepcopy(cfg.ik_match_table1)
+        self.ik_match_table2 = copy.deepcopy(cfg.ik_match_table2)
+        self.human_root_name = cfg.human_root_name
+        self.robot_root_name = cfg.robot_root_name
+        self.use_ik_match_table1 = cfg.use_ik_match_table1
+        self.use_ik_match_table2 = cfg.use_ik_match_table2
+        self.ground = cfg.ground_height * np.array([0, 0, 1])
+        self.max_iter = 10
+        self.solver = solver          # kept for signature parity; the QP is solved exactly on the GPU
+        self.damping = damping
+
+        self._table: TaskTable = compile_task_table(self._robot, cfg)
+        self.model = self._robot
+        self.tasks1 = [{"frame_name": self._table.task_frames[k], "position_cost": float(self._table.w1[k, 0]),
+                        "orientation_cost": float(self._table.w1[k, 1])}
+                       for k in range(self._table.nt) if self._table.in1[k]]
+        self.tasks2 = [{"frame_name": self._table.task_frames[k], "position_cost": float(self._table.w2[k, 0]),
+                        "orientation_cost": float(self._table.w2[k, 1])}
+                       for k in range(self._table.nt) if self._table.in2[k]]
+        self.pos_offsets1 = {n: self._table.pos_off[i].copy() for i, n in enumerate(self._table.human_names)}
+        self.rot_offsets1 = {n: self._table.rot_off[i].copy() for i, n in enumerate(self._table.human_names)}
+
+        self._lib = _native.load_library()          # raises NativeLibraryMissing: no CPU fallback
+        self._handles: Dict[int, _Handle] = {}
+        self._device = self._resolve_device(device)
+
+        self.setup_retarget_configuration()
+
+    # ------------------------------------------------------------------ plumbing ------------
+    @staticmethod
+    def _resolve_device(device) -> int:
+        if device is None:
+            try:
+                import torch
+                return int(torch.cuda.current_device()) if torch.cuda.is_available() else 0
+            except Exception:
+                return 0
+        if isinstance(device, int):
+            return device
+        s = str(device)
+        return int(s.split(":")[1]) if ":" in s else 0
+
+    def _handle(self, device: int) -> _Handle:
+        h = self._handles.get(device)
+        if h is None:
+            desc, keep = _native.build_desc(self._robot, self._table, damping=self.damping, max_iter=self.max_iter)
+            h = _Handle(self._lib, desc, device)
+            del keep
+            self._handles[device] = h
+        return h
+
+    def _invalidate_handles(self) -> None:
+        self._handles = {}
+
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self._lib.gmr_last_error().decode()}")
+
+    # ------------------------------------------------------------------ reference API --------
+    def setup_retarget_configuration(self):
+        """mink.Configuration(model): qpos = qpos0 (motion_retarget.py:74-75)."""
+        self._qpos = np.array(self._robot.qpos0, dtype=np.float64)
+        self.configuration = types.SimpleNamespace(q=self._qpos, model=self._robot,
+                                                   data=types.SimpleNamespace(qpos=self._qpos))
+        self.scaled_human_data = None
+        self._last_frame: Optional[Tuple[np.ndarray, np.ndarray]] = None
+        self._last_ground = False
+        self.last_iters = (0, 0)
+        self.last_errors = (0.0, 0.0)
+
+    def _pack_frame(self, human_data) -> Tuple[np.ndarray, np.ndarray]:
+        names = self._table.human_names
+        pos = np.empty((1, 1, len(names), 3), np.float32)
+        quat = np.empty((1, 1, len(names), 4), np.float32)
+        for i, n in enumerate(names):
+            p, q = human_data[n]          # KeyError for a missing table body, as in the reference (:129/:241)
+            pos[0, 0, i] = np.asarray(p, dtype=np.float64)
+            quat[0, 0, i] = np.asarray(q, dtype=np.float64)
+        return pos, quat
+
+    def _run_single(self, pos: np.ndarray, quat: np.ndarray, flags: int):
+        """One frame through the device entry (float64 or float32 kernel) with the persistent state."""
+        import torch
+        dev = torch.device("cuda", self._device)
+        h = self._handle(self._device)
+        f64 = self.precision == "f64"
+        dt = torch.float64 if f64 else torch.float32
+        nq, nh = self._robot.nq, self._table.nh
+        with torch.cuda.device(dev):
+            d_pos = torch.from_numpy(pos).to(dev)
+            d_quat = torch.from_numpy(quat).to(dev)
+            d_ratio = torch.tensor([self._ratio], dtype=torch.float32, device=dev)
+            d_init = torch.from_numpy(self._qpos.reshape(1, nq)).to(dev, dt)
+            d_q = torch.empty((1, 1, nq), dtype=dt, device=dev)
+            d_it = torch.zeros((1, 1, 2), dtype=torch.int32, device=dev)
+            d_err = torch.zeros((1, 1, 2), dtype=dt, device=dev)
+            d_tg = torch.empty((1, 1, nh, 7), dtype=dt, device=dev)
+            fn = self._lib.gmr_retarget_batch_f64 if f64 else self._lib.gmr_retarget_batch
+            rc = fn(h.ptr, d_pos.data_ptr(), d_quat.data_ptr(), d_ratio.data_ptr(), 1, 1, d_init.data_ptr(),
+                    d_q.data_ptr(), d_it.data_ptr(), d_err.data_ptr(), d_tg.data_ptr(), flags,
+                    torch.cuda.current_stream(dev).cuda_stream)
+            self._check(rc, "gmr_retarget_batch")
+            q = d_q.double().cpu().numpy()[0, 0]
+            it = d_it.cpu().numpy()[0, 0]
+            err = d_err.double().cpu().numpy()[0, 0]
+            tg = d_tg.double().cpu().numpy()[0, 0]
+        return q, it, err, tg
+
+    def _store_targets(self, tg: np.ndarray) -> None:
+        self.scaled_human_data = {n: [tg[i, 0:3].copy(), tg[i, 3:7].copy()]
+                                  for i, n in enumerate(self._table.human_names)}
+
+    def update_targets(self, human_data, offset_to_ground=False):
+        human_data = self.to_numpy(human_data)
+        pos, quat = self._pack_frame(human_data)
+        flags = FLAG_NO_SOLVE | (FLAG_OFFSET_TO_GROUND if offset_to_ground else 0)
+        _, _, err, tg = self._run_single(pos, quat, flags)
+        self._last_frame, self._last_ground = (pos, quat), bool(offset_to_ground)
+        self.last_errors = (float(err[0]), float(err[1]))
+        self._store_targets(tg)
+
+    def retarget(self, human_data, offset_to_ground=False):
+        human_data = self.to_numpy(human_data)
+        pos, quat = self._pack_frame(human_data)
+        flags = FLAG_OFFSET_TO_GROUND if offset_to_ground else 0
+        q, it, err, tg = self._run_single(pos, quat, flags)
+        self._last_frame, self._last_ground = (pos, quat), bool(offset_to_ground)
+        self._qpos[:] = q
+        self.last_iters = (int(it[0]), int(it[1]))
+        self.last_errors = (float(err[0]), float(err[1]))
+        self._store_targets(tg)
+        return self._qpos.copy()
+
+    def _errors_now(self) -> Tuple[float, float]:
+        if self._last_frame is None:
+            raise RuntimeError("target not set: call update_targets() or retarget() first")   # mink TargetNotSet
+        flags = FLAG_NO_SOLVE | (FLAG_OFFSET_TO_GROUND if self._last_ground else 0)
+        _, _, err, _ = self._run_single(self._last_frame[0], self._last_frame[1], flags)
+        return float(err[0]), float(err[1])
+
+    def error1(self):
+        return self._errors_now()[0]
+
+    def error2(self):
+        return self._errors_now()[1]
+
+    # helper methods of the reference, same semantics (host-side, numpy; the batched path does
+    # the same arithmetic inside the kernel)
+    def to_numpy(self, human_data):
+        for body_name in human_data.keys():
+            human_data[body_name] = [np.asarray(human_data[body_name][0]), np.asarray(human_data[body_name][1])]
+        return human_data
+
+    def scale_human_data(self, human_data, human_root_name, human_scale_table):
+        root_pos, root_quat = human_data[human_root_name]
+        scaled_root_pos = human_scale_table[human_root_name] * root_pos
+        out = {human_root_name: (scaled_root_pos, root_quat)}
+        for body_name in human_data.keys():
+            if body_name not in human_scale_table or body_name == human_root_name:
+                continue
+            out[body_name] = ((human_data[body_name][0] - root_pos) * human_scale_table[body_name] + scaled_root_pos,
+                              human_data[body_name][1])
+        return out
+
+    @staticmethod
+    def _qmul(a, b):
+        return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3],
+                         a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                         a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1],
+                         a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]])
+
+    @staticmethod
+    def _qrot(q, v):
+        u = q[1:4]
+        t = 2.0 * np.cross(u, v)
+        return v + q[0] * t + np.cross(u, t)
+
+    def offset_human_data(self, human_data, pos_offsets, rot_offsets):
+        out = {}
+        for body_name in human_data.keys():
+            pos, quat = human_data[body_name]
+            q = np.asarray(quat, np.float64)
+            q = q / np.linalg.norm(q)
+            r = np.asarray(rot_offsets[body_name], np.float64)
+            updated = self._qmul(q, r / np.linalg.norm(r))
+            updated = updated / np.linalg.norm(updated)
+            out[body_name] = [np.asarray(pos, np.float64) + self._qrot(updated, np.asarray(pos_offsets[body_name], np.float64)), updated]
+        return out
+
+    def offset_human_data_to_ground(self, human_data):
+        lowest = np.inf
+        for body_name in human_data.keys():
+            if "Foot" not in body_name and "foot" not in body_name:
+                continue
+            if human_data[body_name][0][2] < lowest:
+                lowest = human_data[body_name][0][2]
+        return {b: [p - np.array([0, 0, lowest]) + np.array([0, 0, 0.1]), q] for b, (p, q) in human_data.items()}
+
+    # ------------------------------------------------------------------ batched entry ---------
+    @property
+    def human_body_names(self) -> List[str]:
+        """Order of the ``nh`` axis of the batched inputs (= ``human_scale_table`` keys)."""
+        return list(self._table.human_names)
+
+    def pack_clips(self, clips: Sequence[Sequence[dict]]) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """list of reference-format clips (list of per-frame dicts) → (pos, quat, lengths), padded to
+        the longest clip by repeating the last frame."""
+        names = self._table.human_names
+        lengths = np.array([len(c) for c in clips], np.int32)
+        T = int(lengths.max()) if len(clips) else 0
+        pos = np.zeros((len(clips), T, len(names), 3), np.float32)
+        quat = np.zeros((len(clips), T, len(names), 4), np.float32)
+        quat[..., 0] = 1.0
+        for ci, clip in enumerate(clips):
+            for t, frame in enumerate(clip):
+                for i, n in enumerate(names):
+                    p, q = frame[n]
+                    pos[ci, t, i] = p
+                    quat[ci, t, i] = q
+            if 0 < len(clip) < T:
+                pos[ci, len(clip):] = pos[ci, len(clip) - 1]
+                quat[ci, len(clip):] = quat[ci, len(clip) - 1]
+        return pos, quat, lengths
+
+    def retarget_batch(self, pos, quat=None, heights=None, qpos_init=None, offset_to_ground: bool = False,
+                       return_info: bool = False, precision: Optional[str] = None, out=None):
+        """Retarget C clips of T frames.
+
+        pos [C,T,nh,3] metres world Z-up, quat [C,T,nh,4] wxyz, bodies ordered as
+        ``human_body_names``; ``heights`` [C] = actual_human_height per clip (None: the instance's
+        own height ratio).  torch CUDA tensors are solved in place on their device and stream
+        (no host copies) and a torch tensor is returned; numpy arrays go through the library's
+        host-buffer pipeline and numpy is returned.  A list of reference-format clips is packed
+        first.  `out` (host path): preallocated float32 [C,T,nq] array, e.g. pinned memory.
+        Returns qpos [C,T,nq] (float32, or float64 with precision='f64'); with
+        return_info also (iters [C,T,2] int32, err [C,T,2])."""
+        if quat is None:
+            pos, quat, _ = self.pack_clips(pos)
+        precision = precision or "f32"
+        flags = FLAG_OFFSET_TO_GROUND if offset_to_ground else 0
+        nq, nh = self._robot.nq, self._table.nh
+        if tuple(pos.shape[2:]) != (nh, 3) or tuple(quat.shape[2:]) != (nh, 4) or tuple(pos.shape[:2]) != tuple(quat.shape[:2]):
+            raise ValueError(f"expected pos [C,T,{nh},3] and quat [C,T,{nh},4], got {tuple(pos.shape)} and {tuple(quat.shape)}")
+        Cn, T = int(pos.shape[0]), int(pos.shape[1])
+
+        if _is_torch(pos):
+            import torch
+            if not pos.is_cuda:
+                raise ValueError("torch inputs must be CUDA tensors (pass numpy arrays for host buffers)")
+            dev = pos.device
+            h = self._handle(dev.index if dev.index is not None else torch.cuda.current_device())
+            f64 = precision == "f64"
+            dt = torch.float64 if f64 else torch.float32
+            with torch.cuda.device(dev):
+                d_pos = pos.to(torch.float32).contiguous()
+                d_quat = quat.to(dev, torch.float32).contiguous()
+                if heights is None:
+                    d_ratio = torch.full((Cn,), self._ratio, dtype=torch.float32, device=dev)
+                else:
+                    d_ratio = (torch.as_tensor(heights, device=dev).to(torch.float32) / float(self._cfg.human_height_assumption)).contiguous()
+                d_init = None if qpos_init is None else torch.as_tensor(qpos_init, device=dev).to(dt).contiguous()
+                d_q = torch.empty((Cn, T, nq), dtype=dt, device=dev)
+                d_it = torch.zeros((Cn, T, 2), dtype=torch.int32, device=dev) if return_info else None
+                d_err = torch.zeros((Cn, T, 2), dtype=dt, device=dev) if return_info else None
+                fn = self._lib.gmr_retarget_batch_f64 if f64 else self._lib.gmr_retarget_batch
+                rc = fn(h.ptr, d_pos.data_ptr(), d_quat.data_ptr(), d_ratio.data_ptr(), Cn, T,
+                        None if d_init is None else d_init.data_ptr(), d_q.data_ptr(),
+                        None if d_it is None else d_it.data_ptr(), None if d_err is None else d_err.data_ptr(),
+                        None, flags, torch.cuda.current_stream(dev).cuda_stream)
+                self._check(rc, "gmr_retarget_batch")
+            return (d_q, d_it, d_err) if return_info else d_q
+
+        # host buffers
+        if precision == "f64":
+            raise ValueError("the host-buffer entry is float32; pass CUDA tensors for precision='f64'")
+        h = self._handle(self._device)
+        a_pos = np.ascontiguousarray(pos, np.float32)
+        a_quat = np.ascontiguousarray(quat, np.float32)
+        if heights is None:
+            a_ratio = np.full((Cn,), self._ratio, np.float32)
+        else:
+            a_ratio = np.ascontiguousarray(np.asarray(heights, np.float32) / np.float32(self._cfg.human_height_assumption), np.float32)
+        a_init = None if qpos_init is None else np.ascontiguousarray(qpos_init, np.float32)
+        if out is not None:
+            if out.dtype != np.float32 or tuple(out.shape) != (Cn, T, nq) or not out.flags.c_contiguous:
+                raise ValueError(f"out must be a C-contiguous float32 array of shape {(Cn, T, nq)}")
+            qpos = out
+        else:
+            qpos = np.empty((Cn, T, nq), np.float32)
+        iters = np.zeros((Cn, T, 2), np.int32) if return_info else None
+        err = np.zeros((Cn, T, 2), np.float32) if return_info else None
+        rc = self._lib.gmr_retarget_batch_host(
+            h.ptr, a_pos.ctypes.data, a_quat.ctypes.data, a_ratio.ctypes.data, Cn, T,
+            None if a_init is None else a_init.ctypes.data, qpos.ctypes.data,
+            None if iters is None else iters.ctypes.data, None if err is None else err.ctypes.data, flags)
+        self._check(rc, "gmr_retarget_batch_host")
+        return (qpos, iters, err) if return_info else qpos

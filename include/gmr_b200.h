@@ -31,6 +31,8 @@ extern "C" {
 
 /* flags for gmr_retarget_batch */
 #define GMR_FLAG_OFFSET_TO_GROUND  1u  /* retarget(..., offset_to_ground=True), motion_retarget.py:122-123,252-270 */
+#define GMR_FLAG_NO_SOLVE          2u  /* update_targets()/error1()/error2() only: targets_out and err_out at the given
+                                         configuration, qpos_out = qpos_init, no IK step (motion_retarget.py:117-136,188-200) */
 
 /*
  * Flat description of one (source format, robot) pair: what the reference constructor
@@ -126,6 +128,9 @@ int gmr_kernel_info(GmrModel* model, int32_t precision_bits, int32_t* threads_pe
                     int32_t* ctas_per_sm);
 
 /* ---- oracle/liboracle.so (CPU checker; test infrastructure only) ----------------------- */
+
+/* oracle-only flag: evaluate mink's SO3/SE3 Jacobian coefficients with cancellation-free forms */
+#define GMR_ORACLE_FLAG_STABLE_LIE 0x10000u
 
 /* Same semantics computed on the host in float64 (precision_bits = 64) or with every
  * arithmetic step in float32 (32, used to study rounding).  Host pointers.  nthreads <= 0

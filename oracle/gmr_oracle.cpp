@@ -104,10 +104,15 @@ template <typename R> void se3_log(const Q4<R>& q, const V3<R>& t, R out[6]) {  
   out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = om[0]; out[4] = om[1]; out[5] = om[2];
 }
 
+// mink's closed forms cancel catastrophically for tiny angles (see gmr_oracle.py STABLE_LIE);
+// g_stable_lie switches to the well-conditioned, mathematically identical forms.
+static bool g_stable_lie = false;
+
 template <typename R> void so3_ljacinv(const R om[3], R J[9]) {                       // mink SO3.ljacinv
   const R eps = Eps<R>::v;
   R th = std::sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]), A;
   if (th < eps) { R t2 = th * th; A = R(1) / R(12) * (R(1) + t2 / R(60) * (R(1) + t2 / R(42) * (R(1) + t2 / R(40)))); }
+  else if (g_stable_lie) { R h = R(0.5) * th; A = (R(1) - h * std::cos(h) / std::sin(h)) / (th * th); }
   else A = (R(1) / (th * th)) * (R(1) - (th * std::sin(th) / (R(2) * (R(1) - std::cos(th)))));
   R S[9], S2[9]; skew(om, S); mm3(S, S, S2);
   for (int i = 0; i < 9; i++) J[i] = (i % 4 == 0 ? R(1) : R(0)) - R(0.5) * S[i] + A * S2[i];
@@ -122,6 +127,11 @@ template <typename R> void se3_ljacinv(const R xi[6], R J[36]) {                
   R th = std::sqrt(th2), s = std::sin(th), c = std::cos(th);
   R B = (th - s) / (th2 * th), C = (R(1) - th2 / R(2) - c) / (th2 * th2),
     D = (R(2) * th - R(3) * s + th * c) / (R(2) * th2 * th2 * th);
+  if (g_stable_lie && th2 < R(0.0625)) {
+    B = R(1) / R(6) - th2 * (R(1) / R(120) - th2 * (R(1) / R(5040) - th2 / R(362880)));
+    C = -R(1) / R(24) + th2 * (R(1) / R(720) - th2 * (R(1) / R(40320) - th2 / R(3628800)));
+    D = R(1) / R(120) - th2 * (R(1) / R(2520) - th2 * (R(1) / R(120960) - th2 / R(9979200)));
+  }
   R V[9], W[9], VW[9], WV[9], WVW[9], VWW[9], VWWt[9], WVWW[9], WWVW[9], Q[9];
   skew(rho, V); skew(om, W); mm3(V, W, VW); tr3(VW, WV); mm3(WV, W, WVW); mm3(VW, W, VWW); tr3(VWW, VWWt);
   mm3(WVW, W, WVWW); mm3(W, WVW, WWVW);
@@ -452,6 +462,7 @@ extern "C" int gmr_oracle_retarget_batch(const GmrModelDesc* desc, const float* 
                                          uint32_t flags, int32_t nthreads, int32_t precision_bits) {
   if (!desc || !pos || !quat || !qpos_out || C < 0 || T < 0) return GMR_EINVAL;
   if (desc->nbody > MAXB || desc->nhinge > MAXH || desc->nhuman > MAXN || desc->ntask > MAXT) return GMR_ELIMIT;
+  g_stable_lie = (flags & GMR_ORACLE_FLAG_STABLE_LIE) != 0;
   if (precision_bits == 32)
     return run_batch<float>(desc, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out, flags, nthreads);
   return run_batch<double>(desc, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out, flags, nthreads);

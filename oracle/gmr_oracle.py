@@ -118,12 +118,25 @@ def so3_log(q: np.ndarray) -> np.ndarray:
     return atan_factor * q[1:]
 
 
+# mink evaluates J_l^{-1} and Barfoot's Q with closed forms that cancel catastrophically for
+# tiny angles (1 - cos θ, θ - sin θ …): for θ ~ 1e-6 rad the coefficient A below carries an
+# absolute error ~1e-16/θ^4 and the Jacobian entries ~1e-4.  LITERAL = the formulas as mink
+# writes them (the faithful restatement, default).  STABLE_LIE = True switches to
+# mathematically identical, well-conditioned forms (half-angle cotangent, power series below
+# 0.25 rad); tests use it to show which part of a GPU-vs-oracle difference is the reference's
+# own rounding noise.
+STABLE_LIE = False
+
+
 def so3_ljacinv(omega: np.ndarray) -> np.ndarray:
     """SO3 inverse left Jacobian J_l^{-1}(ω) (A9)."""
     theta = math.sqrt(float(omega @ omega))
     if theta < _EPS64:
         t2 = theta * theta
         A = (1.0 / 12.0) * (1.0 + t2 / 60.0 * (1.0 + t2 / 42.0 * (1.0 + t2 / 40.0)))
+    elif STABLE_LIE:
+        half = 0.5 * theta
+        A = (1.0 - half * math.cos(half) / math.sin(half)) / (theta * theta)
     else:
         A = (1.0 / theta ** 2) * (1.0 - (theta * math.sin(theta) / (2.0 * (1.0 - math.cos(theta)))))
     S = skew(omega)
@@ -152,7 +165,12 @@ def _se3_getQ(c: np.ndarray) -> np.ndarray:
     if theta_sq < _EPS64:
         B = 1.0 / 6.0 + theta_sq / 120.0
         C = -1.0 / 24.0 + theta_sq / 720.0
-        D = -1.0 / 60.0
+        D = 1.0 / 120.0          # limit of the closed form below (Barfoot's 4th coefficient)
+    elif STABLE_LIE and theta_sq < 0.0625:
+        t2 = theta_sq
+        B = 1.0 / 6.0 - t2 * (1.0 / 120.0 - t2 * (1.0 / 5040.0 - t2 / 362880.0))
+        C = -1.0 / 24.0 + t2 * (1.0 / 720.0 - t2 * (1.0 / 40320.0 - t2 / 3628800.0))
+        D = 1.0 / 120.0 - t2 * (1.0 / 2520.0 - t2 * (1.0 / 120960.0 - t2 / 9979200.0))
     else:
         theta = math.sqrt(theta_sq)
         s, co = math.sin(theta), math.cos(theta)

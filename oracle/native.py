@@ -17,6 +17,8 @@ from general_motion_retargeting_b200._native import GmrModelDesc, build_desc
 HERE = pathlib.Path(__file__).parent
 LIB = HERE / "liboracle.so"
 _lib = None
+FLAG_OFFSET_TO_GROUND = 1
+FLAG_STABLE_LIE = 0x10000     # oracle-only: cancellation-free SO3/SE3 Jacobian coefficients (gmr_oracle.py STABLE_LIE)
 
 
 def build(force: bool = False) -> None:

@@ -17,17 +17,19 @@ static int run(const GmrModelDesc* d, const float* pos, const float* quat, const
   const char* why = nullptr;
   int rc = gmr_fill_consts<R>(d, mc, &why);
   if (rc != GMR_OK) { delete mc; return rc; }
-  GmrWarpLayout lay = gmr_warp_layout(mc->nb, mc->nh, mc->nhum, mc->nt);
+  const GmrDims dims = gmr_dims_of(*mc);
+  const GmrScal<R> ks = gmr_scal_of(*mc);
+  const int wel = gmr_warp_elems<R>(dims.nb, dims.nh, dims.nhum, dims.nt);
   if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
   if (nthreads > C) nthreads = C > 0 ? C : 1;
   std::atomic<int> next{0};
   std::atomic<int64_t> refac{0};
   auto work = [&]() {
-    std::vector<R> sm((size_t)lay.total + 16, R(0));
+    std::vector<R> sm((size_t)wel + 16, R(0));
     for (;;) {
       int c = next.fetch_add(1);
       if (c >= C) break;
-      auto* ws = new WarpSolver<R>(*mc, sm.data());
+      auto* ws = new WarpSolver<R>(*mc, dims, ks, sm.data());
       size_t f0 = (size_t)c * T;
       ws->template run_clip<double>(pos + f0 * mc->nhum * 3, quat + f0 * mc->nhum * 4, ratio ? R(ratio[c]) : R(1), T,
                                     qpos_init ? qpos_init + (size_t)c * mc->nq : nullptr, qpos_out + f0 * mc->nq,

@@ -1,0 +1,52 @@
+import ctypes as C
+import os
+
+import numpy as np
+
+from general_motion_retargeting_b200 import params
+from general_motion_retargeting_b200._native import build_desc
+from general_motion_retargeting_b200.ik_config import compile_task_table
+from general_motion_retargeting_b200.synthetic import make_clips
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu", "libgmr_emu.so")
+_emu = None
+
+
+def problem(src, robot):
+    m, cfg, pack = params.load_pack(src, robot)
+    return m, compile_task_table(m, cfg), pack
+
+
+def emu_retarget_batch(robot, table, pos, quat, ratio, bits=64, flags=0, qpos_init=None, max_iter=10, nthreads=0):
+    """Lane-serial host build of the kernel body (tests/emu) — a debugging aid, not a product path."""
+    global _emu
+    if _emu is None:
+        _emu = C.CDLL(EMU)
+        _emu.gmr_emu_retarget_batch.restype = C.c_int
+    Cn, T = pos.shape[:2]
+    desc, keep = build_desc(robot, table, max_iter=max_iter)
+    qpos = np.zeros((Cn, T, robot.nq)); iters = np.zeros((Cn, T, 2), np.int32); err = np.zeros((Cn, T, 2))
+    tg = np.zeros((Cn, T, table.nh, 7)); refac = C.c_int64(0)
+    pos = np.ascontiguousarray(pos, np.float32); quat = np.ascontiguousarray(quat, np.float32)
+    ratio = None if ratio is None else np.ascontiguousarray(ratio, np.float32)
+    qi = None if qpos_init is None else np.ascontiguousarray(qpos_init, np.float64)
+    rc = _emu.gmr_emu_retarget_batch(
+        C.byref(desc), C.c_void_p(pos.ctypes.data), C.c_void_p(quat.ctypes.data),
+        None if ratio is None else C.c_void_p(ratio.ctypes.data), Cn, T,
+        None if qi is None else C.c_void_p(qi.ctypes.data), C.c_void_p(qpos.ctypes.data),
+        C.c_void_p(iters.ctypes.data), C.c_void_p(err.ctypes.data), C.c_void_p(tg.ctypes.data), flags, nthreads, bits,
+        C.byref(refac))
+    assert rc == 0, rc
+    return qpos, iters, err, tg, refac.value
+
+
+def compare(q, it, q_ref, it_ref):
+    """(agreement rate of iteration counts, max|dq| over all frames, max|dq| over frames whose
+    counts agree and that follow an agreeing frame)."""
+    same = (it == it_ref).all(-1)
+    dq = np.abs(q - q_ref).max(-1)
+    prev_same = np.ones_like(same)
+    prev_same[:, 1:] = same[:, :-1]
+    clean = same & prev_same
+    return float(same.mean()), float(dq.max()), float(dq[clean].max()) if clean.any() else 0.0

@@ -1,0 +1,113 @@
+"""The kernel's algorithm (csrc/gmr_solver.cuh), built lane-serially for the host (tests/emu),
+against the float64 oracle.  This exercises every phase of the warp solver — composite
+"spring inertia" assembly, register-row Cholesky, warm-started active set, flattened
+stage loop — on CPU; the GPU tests repeat the comparison on the real kernel."""
+import numpy as np
+import pytest
+
+from conftest import ALL_PAIRS
+from helpers import compare, emu_retarget_batch, problem
+from general_motion_retargeting_b200.synthetic import make_clips
+
+
+@pytest.mark.parametrize("src,robot", ALL_PAIRS)
+def test_emulated_kernel_matches_oracle_f64(built, src, robot):
+    from oracle import native
+    m, tt, _ = problem(src, robot)
+    clips = make_clips(m, tt, range(4), T=25, src_human=src)
+    q, it, err, tg, _ = emu_retarget_batch(m, tt, clips.pos, clips.quat, clips.ratio(tt), bits=64)
+    # (1) the literal restatement of mink's formulas: the gate of BASELINE.json (1e-3 rad).  mink's
+    #     closed forms for J_l^-1 / Q cancel for tiny rotation errors, which alone moves qpos by ~1e-4.
+    q_ref, it_ref, err_ref = native.retarget_batch(m, tt, clips.pos, clips.quat, clips.ratio(tt))
+    agree, dq_all, dq_clean = compare(q, it, q_ref, it_ref)
+    assert agree == 1.0
+    assert dq_all < 1e-3, dq_all
+    # (2) the same oracle with cancellation-free coefficients: float64 kernel arithmetic is exact to rounding
+    q_st, it_st, err_st = native.retarget_batch(m, tt, clips.pos, clips.quat, clips.ratio(tt), flags=native.FLAG_STABLE_LIE)
+    agree, dq_all, dq_clean = compare(q, it, q_st, it_st)
+    assert agree == 1.0
+    assert dq_all < 1e-9, dq_all
+    np.testing.assert_allclose(err, err_st, atol=1e-9)
+    assert np.abs(np.linalg.norm(q[..., 3:7], axis=-1) - 1).max() < 1e-12
+    assert (q[..., 7:] >= m.hinge_lo - 1e-7).all() and (q[..., 7:] <= m.hinge_hi + 1e-7).all()
+
+
+@pytest.mark.parametrize("src,robot", [("smplx", "unitree_g1"), ("bvh", "booster_t1"), ("smplx", "hightorque_hi")])
+def test_emulated_kernel_f32_within_tolerance(built, src, robot):
+    """BASELINE.json tolerance: max |dqpos| <= 1e-3 rad on identical inputs and iteration counts."""
+    from oracle import native
+    m, tt, _ = problem(src, robot)
+    clips = make_clips(m, tt, range(16), T=40, src_human=src)
+    q_ref, it_ref, _ = native.retarget_batch(m, tt, clips.pos, clips.quat, clips.ratio(tt))
+    q, it, err, tg, _ = emu_retarget_batch(m, tt, clips.pos, clips.quat, clips.ratio(tt), bits=32)
+    agree, dq_all, dq_clean = compare(q, it, q_ref, it_ref)
+    assert agree > 0.995
+    assert dq_clean < 1e-3, dq_clean
+
+
+@pytest.mark.parametrize("src,robot", [("smplx", "stanford_toddy"), ("bvh", "booster_t1"), ("smplx", "unitree_g1")])
+def test_active_set_path_on_unreachable_targets(built, src, robot):
+    """Stress clips (5 cm / 0.3 rad noise) drive joints into their limits: the warm-started
+    primal active set must land on the same (unique) optimum as the oracle's solver."""
+    from oracle import native
+    m, tt, _ = problem(src, robot)
+    clips = make_clips(m, tt, range(6), T=20, src_human=src, stress=True)
+    q_ref, it_ref, _ = native.retarget_batch(m, tt, clips.pos, clips.quat, clips.ratio(tt))
+    q, it, err, tg, nfac = emu_retarget_batch(m, tt, clips.pos, clips.quat, clips.ratio(tt), bits=64)
+    agree, dq_all, dq_clean = compare(q, it, q_ref, it_ref)
+    assert nfac > it.sum()                       # some solves needed more than one factorisation
+    assert agree > 0.99 and dq_clean < 1e-3
+    q_st, it_st, _ = native.retarget_batch(m, tt, clips.pos, clips.quat, clips.ratio(tt), flags=native.FLAG_STABLE_LIE)
+    agree, dq_all, dq_clean = compare(q, it, q_st, it_st)
+    assert agree > 0.99 and dq_clean < 1e-8, dq_clean
+    on_limit = (np.abs(q[..., 7:] - m.hinge_lo) < 1e-6) | (np.abs(q[..., 7:] - m.hinge_hi) < 1e-6)
+    assert on_limit.any() or (q_ref[..., 7:] - m.hinge_lo).min() < 1e-3 or (m.hinge_hi - q_ref[..., 7:]).min() < 1e-3
+
+
+def test_targets_out_no_solve_qpos_init_and_ground(built):
+    from oracle import native
+    import oracle.gmr_oracle as O
+    m, tt, pack = problem("smplx", "unitree_g1")
+    clips = make_clips(m, tt, [4], T=10)
+    ratio = clips.ratio(tt)
+    # targets_out = scaled_human_data of the oracle
+    q, it, err, tg, _ = emu_retarget_batch(m, tt, clips.pos, clips.quat, ratio, bits=64)
+    o = O.OracleRetargeter(m, pack["ik_config"], float(ratio[0]) * tt.height_assumption)
+    frame = {n: (clips.pos[0, 3, i].astype(float), clips.quat[0, 3, i].astype(float)) for i, n in enumerate(tt.human_names)}
+    o.update_targets(frame)
+    for i, n in enumerate(tt.human_names):
+        np.testing.assert_allclose(tg[0, 3, i, :3], o.scaled_human_data[n][0], atol=1e-12)
+        np.testing.assert_allclose(tg[0, 3, i, 3:], o.scaled_human_data[n][1], atol=1e-12)
+    # splitting a clip in two calls chained through qpos_init == one call (warm start is the only state)
+    qa, ita, _, _, _ = emu_retarget_batch(m, tt, clips.pos[:, :6], clips.quat[:, :6], ratio, bits=64)
+    qb, itb, _, _, _ = emu_retarget_batch(m, tt, clips.pos[:, 6:], clips.quat[:, 6:], ratio, bits=64, qpos_init=qa[:, -1])
+    np.testing.assert_allclose(np.concatenate([qa, qb], 1), q, atol=1e-9)
+    np.testing.assert_array_equal(np.concatenate([ita, itb], 1), it)
+    # NO_SOLVE: qpos untouched, errors = error1()/error2() at that configuration
+    qn, itn, errn, _, _ = emu_retarget_batch(m, tt, clips.pos[:, 6:7], clips.quat[:, 6:7], ratio, bits=64, qpos_init=qa[:, -1], flags=2)
+    np.testing.assert_allclose(qn[:, 0], qa[:, -1], atol=0)
+    assert (itn == 0).all()
+    o2 = O.OracleRetargeter(m, pack["ik_config"], float(ratio[0]) * tt.height_assumption)
+    o2.qpos[:] = qa[0, -1]; o2._fk()
+    frame = {n: (clips.pos[0, 6, i].astype(float), clips.quat[0, 6, i].astype(float)) for i, n in enumerate(tt.human_names)}
+    o2.update_targets(frame)
+    np.testing.assert_allclose(errn[0, 0], [o2.error1(), o2.error2()], atol=1e-9)
+    # offset_to_ground flag
+    qg_ref, itg_ref, _ = native.retarget_batch(m, tt, clips.pos, clips.quat, ratio, flags=1 | native.FLAG_STABLE_LIE)
+    qg, itg, _, _, _ = emu_retarget_batch(m, tt, clips.pos, clips.quat, ratio, bits=64, flags=1)
+    np.testing.assert_array_equal(itg, itg_ref)
+    np.testing.assert_allclose(qg, qg_ref, atol=1e-9)
+    assert np.abs(qg - q).max() > 1e-3
+
+
+def test_single_stage_and_iteration_cap(built):
+    from oracle import native
+    m, tt, _ = problem("smplx", "kuavo_s45")         # use_ik_match_table2 = false
+    clips = make_clips(m, tt, [0, 1], T=12)
+    q, it, err, _, _ = emu_retarget_batch(m, tt, clips.pos, clips.quat, clips.ratio(tt), bits=64)
+    assert (it[..., 1] == 0).all() and (it[..., 0] >= 1).all() and it.max() <= 11
+    # max_iter = 0: exactly one solve per enabled stage
+    m, tt, _ = problem("smplx", "unitree_g1")
+    clips = make_clips(m, tt, [0], T=5)
+    q, it, err, _, _ = emu_retarget_batch(m, tt, clips.pos, clips.quat, clips.ratio(tt), bits=64, max_iter=0)
+    assert (it == 1).all()

@@ -1,0 +1,259 @@
+"""Parity tests proper: the sm_100a kernels, called through the C ABI (ctypes on
+libgmr_b200.so) and through the reference-facing Python class, against the CPU oracle."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ALL_PAIRS
+from helpers import compare, problem
+from general_motion_retargeting_b200.synthetic import make_clips
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from general_motion_retargeting_b200 import _native
+    return _native.load_library()      # raises if the CUDA extension is missing: no fallback
+
+
+def capi_run(lib, torch, robot, table, pos, quat, ratio, bits=32, flags=0, qpos_init=None, want_targets=False):
+    """gmr_model_create + gmr_retarget_batch[_f64] with raw device pointers."""
+    from general_motion_retargeting_b200._native import build_desc
+    desc, keep = build_desc(robot, table)
+    h = C.c_void_p()
+    assert lib.gmr_model_create(C.byref(desc), 0, C.byref(h)) == 0, lib.gmr_last_error()
+    try:
+        dev = torch.device("cuda", 0)
+        dt = torch.float64 if bits == 64 else torch.float32
+        Cn, T = pos.shape[:2]
+        d_pos, d_quat = torch.from_numpy(np.ascontiguousarray(pos)).to(dev), torch.from_numpy(np.ascontiguousarray(quat)).to(dev)
+        d_ratio = torch.from_numpy(np.ascontiguousarray(ratio, np.float32)).to(dev)
+        d_init = None if qpos_init is None else torch.from_numpy(np.ascontiguousarray(qpos_init)).to(dev, dt)
+        d_q = torch.zeros((Cn, T, robot.nq), dtype=dt, device=dev)
+        d_it = torch.zeros((Cn, T, 2), dtype=torch.int32, device=dev)
+        d_err = torch.zeros((Cn, T, 2), dtype=dt, device=dev)
+        d_tg = torch.zeros((Cn, T, table.nh, 7), dtype=dt, device=dev) if want_targets else None
+        fn = lib.gmr_retarget_batch_f64 if bits == 64 else lib.gmr_retarget_batch
+        rc = fn(h, d_pos.data_ptr(), d_quat.data_ptr(), d_ratio.data_ptr(), Cn, T,
+                None if d_init is None else d_init.data_ptr(), d_q.data_ptr(), d_it.data_ptr(), d_err.data_ptr(),
+                None if d_tg is None else d_tg.data_ptr(), flags, torch.cuda.current_stream(dev).cuda_stream)
+        assert rc == 0, lib.gmr_last_error()
+        torch.cuda.synchronize(dev)
+        out = (d_q.double().cpu().numpy(), d_it.cpu().numpy(), d_err.double().cpu().numpy())
+        return out + ((d_tg.double().cpu().numpy(),) if want_targets else ())
+    finally:
+        lib.gmr_model_destroy(h)
+
+
+@pytest.mark.parametrize("src,robot", ALL_PAIRS)
+def test_f64_kernel_matches_oracle(lib, torch_cuda, src, robot):
+    from oracle import native
+    m, tt, _ = problem(src, robot)
+    clips = make_clips(m, tt, range(8), T=30, src_human=src)
+    ratio = clips.ratio(tt)
+    q, it, err = capi_run(lib, torch_cuda, m, tt, clips.pos, clips.quat, ratio, bits=64)
+    q_ref, it_ref, err_ref = native.retarget_batch(m, tt, clips.pos, clips.quat, ratio)
+    agree, dq_all, dq_clean = compare(q, it, q_ref, it_ref)
+    assert agree >= 0.995 and dq_clean < 1e-3, (agree, dq_clean)          # BASELINE.json gate
+    q_st, it_st, err_st = native.retarget_batch(m, tt, clips.pos, clips.quat, ratio, flags=native.FLAG_STABLE_LIE)
+    agree, dq_all, dq_clean = compare(q, it, q_st, it_st)
+    assert agree == 1.0 and dq_all < 1e-8, (agree, dq_all)                # exact up to rounding
+    np.testing.assert_allclose(err, err_st, atol=1e-8)
+
+
+@pytest.mark.parametrize("src,robot", ALL_PAIRS)
+def test_f32_kernel_within_tolerance(lib, torch_cuda, src, robot):
+    """max |dqpos| <= 1e-3 rad on identical synthetic inputs and iteration counts (BASELINE.json);
+    task-error parity <= 1e-4 m."""
+    from oracle import native
+    m, tt, _ = problem(src, robot)
+    clips = make_clips(m, tt, range(16), T=40, src_human=src)
+    ratio = clips.ratio(tt)
+    q, it, err = capi_run(lib, torch_cuda, m, tt, clips.pos, clips.quat, ratio, bits=32)
+    q_ref, it_ref, err_ref = native.retarget_batch(m, tt, clips.pos, clips.quat, ratio)
+    agree, dq_all, dq_clean = compare(q, it, q_ref, it_ref)
+    assert agree >= 0.99, agree
+    assert dq_clean < 1e-3, dq_clean
+    same = (it == it_ref).all(-1)
+    assert np.abs(err - err_ref)[same].max() < 1e-4
+
+
+def test_known_answer_vectors(lib, torch_cuda):
+    """tests/golden/oracle_traces.npz: committed float64 oracle traces (incl. stress clips that
+    run the active-set path and the single-stage kuavo config)."""
+    g = np.load(os.path.join(GOLD, "oracle_traces.npz"))
+    for key in sorted({k.rsplit(".", 1)[0] for k in g.files}):
+        src, robot = key.split("_", 1)
+        m, tt, _ = problem(src, robot)
+        ratio = (g[key + ".heights"] / np.float32(tt.height_assumption)).astype(np.float32)
+        for bits, tol in ((64, 1e-3), (32, 1e-3)):
+            q, it, err = capi_run(lib, torch_cuda, m, tt, g[key + ".pos"], g[key + ".quat"], ratio, bits=bits)
+            agree, dq_all, dq_clean = compare(q, it, g[key + ".qpos"], g[key + ".iters"])
+            assert agree >= 0.97 and dq_clean < tol, (key, bits, agree, dq_clean)
+
+
+@pytest.mark.parametrize("src,robot", [("smplx", "stanford_toddy"), ("bvh", "booster_t1"), ("smplx", "unitree_g1")])
+def test_active_set_on_unreachable_targets(lib, torch_cuda, src, robot):
+    from oracle import native
+    m, tt, _ = problem(src, robot)
+    clips = make_clips(m, tt, range(8), T=25, src_human=src, stress=True)
+    ratio = clips.ratio(tt)
+    q, it, err = capi_run(lib, torch_cuda, m, tt, clips.pos, clips.quat, ratio, bits=64)
+    q_st, it_st, _ = native.retarget_batch(m, tt, clips.pos, clips.quat, ratio, flags=native.FLAG_STABLE_LIE)
+    agree, dq_all, dq_clean = compare(q, it, q_st, it_st)
+    assert agree >= 0.99 and dq_clean < 1e-7, (agree, dq_clean)
+    assert (q[..., 7:] >= m.hinge_lo - 1e-6).all() and (q[..., 7:] <= m.hinge_hi + 1e-6).all()
+
+
+def test_flags_init_state_and_targets(lib, torch_cuda):
+    from oracle import native
+    m, tt, _ = problem("smplx", "unitree_g1")
+    clips = make_clips(m, tt, [4, 5], T=10)
+    ratio = clips.ratio(tt)
+    q, it, err, tg = capi_run(lib, torch_cuda, m, tt, clips.pos, clips.quat, ratio, bits=64, want_targets=True)
+    # chaining two calls through qpos_init == one call
+    qa, ita, _ = capi_run(lib, torch_cuda, m, tt, clips.pos[:, :6], clips.quat[:, :6], ratio, bits=64)
+    qb, itb, _ = capi_run(lib, torch_cuda, m, tt, clips.pos[:, 6:], clips.quat[:, 6:], ratio, bits=64, qpos_init=qa[:, -1])
+    np.testing.assert_array_equal(np.concatenate([ita, itb], 1), it)
+    np.testing.assert_allclose(np.concatenate([qa, qb], 1), q, atol=1e-12)
+    # NO_SOLVE leaves qpos alone and reports the stage errors
+    qn, itn, errn = capi_run(lib, torch_cuda, m, tt, clips.pos[:, 6:7], clips.quat[:, 6:7], ratio, bits=64, qpos_init=qa[:, -1], flags=2)
+    np.testing.assert_array_equal(qn[:, 0], qa[:, -1])
+    assert (itn == 0).all() and (errn > 0).all()
+    # offset_to_ground
+    qg, itg, _ = capi_run(lib, torch_cuda, m, tt, clips.pos, clips.quat, ratio, bits=64, flags=1)
+    qg_ref, itg_ref, _ = native.retarget_batch(m, tt, clips.pos, clips.quat, ratio, flags=1 | native.FLAG_STABLE_LIE)
+    np.testing.assert_array_equal(itg, itg_ref)
+    np.testing.assert_allclose(qg, qg_ref, atol=1e-8)
+    # targets_out are unit quaternions and finite
+    assert np.isfinite(tg).all() and np.abs(np.linalg.norm(tg[..., 3:], axis=-1) - 1).max() < 1e-12
+
+
+def test_c_abi_error_codes(lib, torch_cuda):
+    from general_motion_retargeting_b200._native import build_desc
+    m, tt, _ = problem("smplx", "unitree_g1")
+    desc, keep = build_desc(m, tt)
+    h = C.c_void_p()
+    assert lib.gmr_model_create(None, 0, C.byref(h)) == -1 and b"null" in lib.gmr_last_error()
+    assert lib.gmr_model_create(C.byref(desc), 0, None) == -1
+    assert lib.gmr_model_create(C.byref(desc), 9999, C.byref(h)) == -2          # no such device
+    bad = build_desc(m, tt)[0]; bad.nhinge = 40
+    assert lib.gmr_model_create(C.byref(bad), 0, C.byref(h)) == -4               # GMR_ELIMIT
+    assert lib.gmr_model_create(C.byref(desc), 0, C.byref(h)) == 0
+    assert lib.gmr_retarget_batch(h, None, None, None, 4, 4, None, None, None, None, None, 0, None) == -1
+    assert lib.gmr_retarget_batch(h, None, None, None, 0, 0, None, None, None, None, None, 0, None) == 0   # empty batch
+    assert lib.gmr_retarget_batch(None, None, None, None, 0, 0, None, None, None, None, None, 0, None) == -1
+    assert lib.gmr_model_destroy(h) == 0 and lib.gmr_model_destroy(None) == 0
+
+
+def test_python_class_is_a_drop_in(lib, torch_cuda):
+    """GeneralMotionRetargeting(src, robot, height).retarget(frame) frame by frame == the oracle's
+    reference loop; update_targets / scaled_human_data / error1 / error2 behave like the reference."""
+    import oracle.gmr_oracle as O
+    from general_motion_retargeting_b200 import GeneralMotionRetargeting
+    m, tt, pack = problem("smplx", "unitree_g1")
+    clips = make_clips(m, tt, [11], T=6)
+    height = float(clips.ratio(tt)[0]) * tt.height_assumption
+    O.STABLE_LIE = True
+    try:
+        o = O.OracleRetargeter(m, pack["ik_config"], height)
+        g = GeneralMotionRetargeting("smplx", "unitree_g1", actual_human_height=height)
+        assert g.xml_file.endswith("g1_mocap_29dof.xml") and g.max_iter == 10 and g.damping == 0.5
+        assert set(g.human_scale_table) == set(tt.human_names)
+        for t in range(6):
+            frame = {n: (clips.pos[0, t, i].astype(float), clips.quat[0, t, i].astype(float)) for i, n in enumerate(tt.human_names)}
+            frame2 = {k: (v[0].tolist(), v[1].tolist()) for k, v in frame.items()}       # array-likes, as loaders give
+            frame2["some_other_joint"] = ([0, 0, 0], [1, 0, 0, 0])                        # extras are ignored (:219)
+            q_ref = o.retarget(frame)
+            q = g.retarget(frame2)
+            assert isinstance(frame2["pelvis"][0], np.ndarray)                              # to_numpy mutates the caller's dict (:203-206)
+            assert q.dtype == np.float64 and q.shape == (m.nq,)
+            np.testing.assert_allclose(q, q_ref, atol=1e-6)
+            assert g.last_iters == tuple(o.last_iters)
+            for n in tt.human_names:
+                np.testing.assert_allclose(g.scaled_human_data[n][0], o.scaled_human_data[n][0], atol=1e-6)
+            np.testing.assert_allclose([g.error1(), g.error2()], [o.error1(), o.error2()], atol=1e-6)
+        del frame["left_foot"]
+        with pytest.raises(KeyError):
+            g.retarget(frame)
+    finally:
+        O.STABLE_LIE = False
+
+
+def test_batched_entry_torch_numpy_and_list(lib, torch_cuda):
+    torch = torch_cuda
+    from general_motion_retargeting_b200 import GeneralMotionRetargeting
+    m, tt, _ = problem("bvh", "booster_t1")
+    clips = make_clips(m, tt, range(6), T=12, src_human="bvh")
+    g = GeneralMotionRetargeting("bvh", "booster_t1", actual_human_height=1.75)
+    pos, quat = torch.from_numpy(clips.pos).cuda(), torch.from_numpy(clips.quat).cuda()
+    q_t, it_t, err_t = g.retarget_batch(pos, quat, torch.from_numpy(clips.heights).cuda(), return_info=True)
+    assert q_t.is_cuda and q_t.dtype == torch.float32 and tuple(q_t.shape) == (6, 12, m.nq)
+    q_n = g.retarget_batch(clips.pos, clips.quat, clips.heights)                         # host buffers
+    np.testing.assert_array_equal(q_n, q_t.cpu().numpy())                                # same kernel, same bits
+    q_none = g.retarget_batch(clips.pos, clips.quat)                                     # heights=None -> constructor height
+    np.testing.assert_array_equal(q_none, q_n)
+    # list-of-dict clips of different lengths are padded with their last frame
+    lst = [[{n: (clips.pos[c, t, i], clips.quat[c, t, i]) for i, n in enumerate(tt.human_names)} for t in range(12 - 2 * c)] for c in range(3)]
+    q_l = g.retarget_batch(lst)
+    np.testing.assert_array_equal(q_l[0], q_n[0])
+    np.testing.assert_array_equal(q_l[1, :10], q_n[1, :10])
+    with pytest.raises(ValueError):
+        g.retarget_batch(clips.pos[:, :, :5], clips.quat)
+    out = np.empty((6, 12, m.nq), np.float32)
+    assert g.retarget_batch(clips.pos, clips.quat, clips.heights, out=out) is out
+
+
+def test_full_size_properties(lib, torch_cuda):
+    """BASELINE.json configs[1] size (4096 clips x 300 frames, unitree_g1): size-independent properties —
+    determinism, independence of clips (permutation / sub-batch invariance), limits, unit quaternions —
+    and oracle parity on a slice."""
+    torch = torch_cuda
+    from oracle import native
+    from general_motion_retargeting_b200 import GeneralMotionRetargeting
+    m, tt, _ = problem("smplx", "unitree_g1")
+    Cn, T = 4096, 300
+    clips = make_clips(m, tt, range(Cn), T=T, device="cuda")
+    g = GeneralMotionRetargeting("smplx", "unitree_g1")
+    pos, quat, h = torch.from_numpy(clips.pos).cuda(), torch.from_numpy(clips.quat).cuda(), torch.from_numpy(clips.heights).cuda()
+    q, it, err = g.retarget_batch(pos, quat, h, return_info=True)
+    q2 = g.retarget_batch(pos, quat, h)
+    assert torch.equal(q, q2)                                                             # deterministic
+    perm = torch.randperm(Cn, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
+    q3 = g.retarget_batch(pos[perm], quat[perm], h[perm])
+    assert torch.equal(q3, q[perm])                                                       # clips are independent
+    q4 = g.retarget_batch(pos[100:137], quat[100:137], h[100:137])
+    assert torch.equal(q4, q[100:137])
+    qn = q.cpu().numpy()
+    assert np.isfinite(qn).all()
+    assert np.abs(np.linalg.norm(qn[..., 3:7], axis=-1) - 1).max() < 1e-5
+    assert (qn[..., 7:] >= m.hinge_lo - 1e-4).all() and (qn[..., 7:] <= m.hinge_hi + 1e-4).all()
+    itn = it.cpu().numpy()
+    assert itn.min() >= 1 and itn.max() <= 11
+    assert 3.5 < itn.sum(-1).mean() < 6.0                                                 # ~4 solves per frame
+    # tracking quality: steady-state error norm like the oracle's (~0.05-0.1, dominated by zero-weight rows)
+    assert np.median(err.cpu().numpy()[:, 10:, 1]) < 0.2
+    # oracle parity on 128 clips x 300 frames
+    S = 128
+    q_ref, it_ref, _ = native.retarget_batch(m, tt, clips.pos[:S], clips.quat[:S], clips.ratio(tt)[:S])
+    agree, dq_all, dq_clean = compare(qn[:S].astype(np.float64), itn[:S], q_ref, it_ref)
+    assert agree > 0.995 and dq_clean < 1e-3, (agree, dq_clean)
+    q64, it64, _ = g.retarget_batch(pos[:S], quat[:S], h[:S], return_info=True, precision="f64")
+    agree, dq_all, dq_clean = compare(q64.cpu().numpy(), it64.cpu().numpy(), q_ref, it_ref)
+    assert agree > 0.999 and dq_clean < 1e-3, (agree, dq_clean)
+
+
+def test_smoke_entry(lib, torch_cuda):
+    import __graft_entry__ as ge
+    ge.smoke()

@@ -1,0 +1,63 @@
+"""Multi-rank path on CPU: contiguous clip shards + gloo (world_size 2) for the hand-over."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from general_motion_retargeting_b200.sharding import all_shards, clip_shard
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shards_partition_the_clips():
+    for C in (0, 1, 7, 4096, 65536, 65537):
+        for W in (1, 2, 3, 4, 8):
+            sh = all_shards(C, W)
+            assert sh[0][0] == 0 and sh[-1][1] == C
+            assert all(a[1] == b[0] for a, b in zip(sh, sh[1:]))
+            sizes = [e - b for b, e in sh]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        clip_shard(10, 2, 2)
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["GMR_ROOT"]); sys.path.insert(0, os.path.join(os.environ["GMR_ROOT"], "tests"))
+import numpy as np, torch, torch.distributed as dist
+from helpers import problem, emu_retarget_batch
+from general_motion_retargeting_b200.synthetic import make_clips
+from general_motion_retargeting_b200.sharding import clip_shard, gather_clips, max_over_ranks
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+m, tt, _ = problem("smplx", "unitree_g1")
+C, T = 5, 6
+b, e = clip_shard(C, rank, world)
+clips = make_clips(m, tt, range(b, e), T=T)
+q, it, err, tg, _ = emu_retarget_batch(m, tt, clips.pos, clips.quat, clips.ratio(tt), bits=64)
+full = gather_clips(torch.from_numpy(q), C)
+t = max_over_ranks(float(rank + 1))
+if rank == 0:
+    np.save(os.environ["GMR_OUT"], full.numpy())
+    assert t == float(world)
+dist.destroy_process_group()
+'''
+
+
+def test_two_ranks_over_gloo_equal_one_process(built, tmp_path):
+    from helpers import emu_retarget_batch, problem
+    from general_motion_retargeting_b200.synthetic import make_clips
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    out = tmp_path / "q.npy"
+    env = dict(os.environ, GMR_ROOT=ROOT, GMR_OUT=str(out), OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", str(script)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    m, tt, _ = problem("smplx", "unitree_g1")
+    clips = make_clips(m, tt, range(5), T=6)
+    q, *_ = emu_retarget_batch(m, tt, clips.pos, clips.quat, clips.ratio(tt), bits=64)
+    np.testing.assert_array_equal(np.load(out), q)
