@@ -413,6 +413,12 @@ struct WarpSolver {
               }
             }
           }
+          if (th2 < GmrEps<R>::lie) {
+            // mink's SE3 Jacobian shortcut: for theta^2 < eps, jlog(T) is taken to be the 6x6 identity
+            // (the rho-dependent block Q = [rho]x / 2 is dropped).  Reproduced for parity.
+            GMR_UNROLL
+            for (int i = 0; i < 9; i++) { Ji[i] = ((i & 3) == 0) ? R(1) : R(0); Q[i] = R(0); }
+          }
           R Rb[9]; q_to_mat(qb, Rb);
           m3_mul_bt(Ji, Rb, P);                 // P = Jinv R_b^T
           R T1[9], T2[9];
