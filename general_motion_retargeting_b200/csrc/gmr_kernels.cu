@@ -25,6 +25,7 @@ std::atomic<int64_t> g_launches{0};
 int set_err(int code, const std::string& msg) { g_err = msg; return code; }
 int cuda_err(cudaError_t e, const char* what) {
   g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  (void)cudaGetLastError();      // do not leave a sticky "last error" behind for the caller's next launch
   return GMR_ECUDA;
 }
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return cuda_err(_e, #call); } while (0)
@@ -108,7 +109,10 @@ namespace {
 
 struct DeviceGuard {
   int prev = -1; bool ok = false;
-  explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true; }
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+    else (void)cudaGetLastError();
+  }
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 

@@ -55,11 +55,16 @@
 
 // ---- shared-memory layout of one warp's state (units: elements of R) -----------------------
 GMR_HD constexpr int gmr_pad4(int n) { return (n + 3) & ~3; }
-// offset of pivot row k in the packed factor storage (row k = 6 base columns + k hinge columns,
-// padded to 4): sum_{i<k} pad4(6+i) = 4 * (F(k+8) - F(8)), F(N) = sum_{n<=N} floor(n/4)
-GMR_HD constexpr int gmr_loff(int k) {
-  const int N = k + 8, a = N >> 2, b = N & 3;
-  return 4 * (2 * a * (a - 1) + a * (b + 1) - 6);
+// Packed storage of the factor rows.  Row i (lane i, block b = i / 4) holds
+//   [ a'(6) 0 0 | L_i0 .. L_i,i-1 | -1 at column i | zeros up to the end of its block of 4 columns ]
+// i.e. GMR_LC + 4 (b + 1) values: base columns at 0..5, hinge column m at GMR_LC + m.  The zero
+// tail and the -1 let every lane take a FIXED-LENGTH, statically indexed dot product with the
+// broadcast pivot row:  sum_m row_i[m] * lk[m] = sum_{m<k} L_im L_km - H_ik.
+#define GMR_LC 8
+GMR_HD constexpr int gmr_rlen(int b) { return GMR_LC + 4 * (b + 1); }
+GMR_HD constexpr int gmr_loff(int i) {
+  const int b = i >> 2, e = i & 3;
+  return 8 * b * b + 40 * b + e * (12 + 4 * b);
 }
 
 // fixed part
@@ -84,7 +89,9 @@ template <typename R> GMR_HD int gmr_warp_elems(int nb, int nh, int nhum, int nt
 }
 
 template <typename R> struct GmrEps;
-template <> struct GmrEps<float>  { static constexpr float  lie = 1.1920929e-06f; static constexpr float  lam = 1e-5f;  };
+// `lie` is the reference's float64 threshold (mink get_epsilon(float64) = 10 eps) in BOTH precisions: the branch
+// decisions (Taylor vs closed form, the jlog = I shortcut) must follow the float64 reference, not the kernel's dtype.
+template <> struct GmrEps<float>  { static constexpr float  lie = 2.220446049250313e-15f; static constexpr float  lam = 1e-5f;  };
 template <> struct GmrEps<double> { static constexpr double lie = 2.220446049250313e-15; static constexpr double lam = 1e-12; };
 
 // per-lane registers that persist across lane blocks (what the factorisation keeps live;
@@ -378,12 +385,13 @@ struct WarpSolver {
           } else {
             const R th = g_sqrt(th2);
             const R n = g_sqrt(nsq);                       // sin(theta/2); qe[0] = cos(theta/2)
-            cV = (R(1) - R(0.5) * th * qe[0] / n) / th2;
             if (th < R(0.25)) {                            // series: the closed forms cancel badly for small theta
+              cV = R(1) / R(12) + th2 * (R(1) / R(720) + th2 * (R(1) / R(30240) + th2 / R(1209600)));
               Bq = R(1) / R(6) - th2 * (R(1) / R(120) - th2 * (R(1) / R(5040) - th2 / R(362880)));
               Cq = -R(1) / R(24) + th2 * (R(1) / R(720) - th2 * (R(1) / R(40320) - th2 / R(3628800)));
               Dq = R(1) / R(120) - th2 * (R(1) / R(2520) - th2 * (R(1) / R(120960) - th2 / R(9979200)));
             } else {
+              cV = (R(1) - R(0.5) * th * qe[0] / n) / th2;
               const R st = R(2) * n * qe[0], ct = qe[0] * qe[0] - nsq;
               Bq = (th - st) / (th2 * th);
               Cq = (R(1) - th2 * R(0.5) - ct) / (th2 * th2);
@@ -544,7 +552,7 @@ struct WarpSolver {
           GMR_UNROLL
           for (int g = 0; g < 6; g++) o[g] = L.a[g] * bv;
           GMR_UNROLL
-          for (int j = 0; j < GMR_NH; j++) if (j < lane) o[6 + j] = L.row[j] * bv;
+          for (int j = 0; j < GMR_NH; j++) if (j < lane) o[GMR_LC + j] = L.row[j] * bv;
         }
       GMR_END
       GMR_LANES
@@ -561,7 +569,7 @@ struct WarpSolver {
             for (int j = 0; j < GMR_NH; j++) {
               if ((pinned >> j) & 1u) {
                 if (j < lane) { r -= L.row[j] * s_bnd()[j]; L.row[j] = R(0); }
-                else if (j > lane && j < dm.nh) r -= s_L()[gmr_loff(j) + 6 + lane];
+                else if (j > lane && j < dm.nh) r -= s_L()[gmr_loff(j) + GMR_LC + lane];
               }
             }
             L.rhs = r;
@@ -641,69 +649,87 @@ struct WarpSolver {
           r -= s * lf[21 + i];
         }
         L.rhs = r;
+        // initialise this lane's packed row: a', two pad zeros, zeros over its hinge columns, -1 on the diagonal
         R* o = s_L() + gmr_loff(lane);
         GMR_UNROLL
         for (int g = 0; g < 6; g++) o[g] = L.a[g];
+        o[6] = R(0); o[7] = R(0);
+        const int nc = 4 * ((lane >> 2) + 1);
+        for (int j = 0; j < nc; j++) o[GMR_LC + j] = (j == lane) ? R(-1) : R(0);
       }
     GMR_END
-    // hinge block, column by column (pivot k unrolled so that row[] stays in registers);
-    // the pivot row (6 base + k hinge entries) is broadcast from shared memory 4 values at a time
-    GMR_UNROLL
-    for (int k = 0; k < GMR_NH; k++) {
-      if (k < dm.nh) {
-        GMR_LANES
-          if (lane >= k && lane < dm.nh) {
-            const R* lk = s_L() + gmr_loff(k);
-            R s = L.row[k];
-            GMR_UNROLL
-            for (int c = 0; c < (6 + k + 3) / 4; c++) {
-              R v[4]; g_ld4(lk + 4 * c, v);
+    // hinge block, column by column.  Blocks of 4 pivots: the outer loop is ROLLED (the code of one
+    // block is reused, which keeps the instruction footprint small), registers are indexed
+    // statically inside a block and the only block-dependent register access — storing the new
+    // column into row[4b+e] — goes through a switch.
+    const int nblk = (dm.nh + 3) >> 2;
+    for (int b = 0; b < nblk; b++) {
+      GMR_UNROLL
+      for (int e = 0; e < 4; e++) {
+        const int k = 4 * b + e;
+        if (k < dm.nh) {
+          GMR_LANES
+            if (lane >= k && lane < dm.nh) {
+              const R* lk = s_L() + gmr_loff(k);
+              R s = R(0);
               GMR_UNROLL
-              for (int e = 0; e < 4; e++) {
-                const int i = 4 * c + e;
-                if (i < 6) s -= L.a[i < 6 ? i : 0] * v[e];
-                else if (i < 6 + k) s -= L.row[(i >= 6 && i < 6 + GMR_NH) ? i - 6 : 0] * v[e];
+              for (int c = 0; c < 2 + GMR_NH / 4; c++) {
+                if (c < 3 + b) {                      // pivot row length = 4 * (3 + b)
+                  R v[4]; g_ld4(lk + 4 * c, v);
+                  GMR_UNROLL
+                  for (int u = 0; u < 4; u++) {
+                    const int p = 4 * c + u;
+                    if (p < 6) s += L.a[p < 6 ? p : 0] * v[u];
+                    else if (p >= GMR_LC) s += L.row[(p >= GMR_LC && p < GMR_LC + GMR_NH) ? p - GMR_LC : 0] * v[u];
+                  }
+                }
+              }
+              s = -s;                                  // = H_ik - sum_{m<k} L_im L_km (base columns included)
+              if (lane == k) {
+                const R d = g_sqrt(s), di = R(1) / d;
+                L.dinv = di;
+                const R y = L.rhs * di;
+                L.rhs = y;
+                s_piv()[0] = di; s_piv()[1] = y;
+              } else {
+                L.tmp = s;
               }
             }
-            if (lane == k) {
-              const R d = g_sqrt(s), di = R(1) / d;
-              L.dinv = di;
-              const R y = L.rhs * di;
-              L.rhs = y;
-              s_piv()[0] = di; s_piv()[1] = y;
-            } else {
-              L.tmp = s;
+          GMR_END
+          GMR_LANES
+            if (lane > k && lane < dm.nh) {
+              const R l = L.tmp * s_piv()[0];
+              switch (b) {
+                case 0: L.row[0 + e] = l; break;
+                case 1: L.row[4 + e] = l; break;
+                case 2: L.row[8 + e] = l; break;
+                case 3: L.row[12 + e] = l; break;
+                case 4: L.row[16 + e] = l; break;
+                case 5: L.row[20 + e] = l; break;
+                case 6: L.row[24 + e] = l; break;
+                default: L.row[28 + e] = l; break;
+              }
+              s_L()[gmr_loff(lane) + GMR_LC + k] = l;
+              L.rhs -= l * s_piv()[1];
             }
-          }
-        GMR_END
-        GMR_LANES
-          if (lane > k && lane < dm.nh) {
-            const R l = L.tmp * s_piv()[0];
-            L.row[k] = l;
-            s_L()[gmr_loff(lane) + 6 + k] = l;
-            L.rhs -= l * s_piv()[1];
-          }
-        GMR_END
+          GMR_END
+        }
       }
     }
     // back substitution: hinges from the last to the first, lanes 0..5 also accumulate A'^T x
     GMR_LANES
       L.tmp = (lane < 6) ? s_lf()[21 + lane] : R(0);      // zf accumulators (lanes 0..5)
     GMR_END
-    GMR_UNROLL
-    for (int kk = 0; kk < GMR_NH; kk++) {
-      const int k = GMR_NH - 1 - kk;
-      if (k < dm.nh) {
-        GMR_LANES
-          if (lane == k) s_xs()[6 + k] = L.rhs * L.dinv;
-        GMR_END
-        GMR_LANES
-          const R x = s_xs()[6 + k];
-          const R* lk = s_L() + gmr_loff(k);
-          if (lane < k) L.rhs -= lk[6 + lane] * x;
-          if (lane < 6) L.tmp -= lk[lane] * x;
-        GMR_END
-      }
+    for (int k = dm.nh - 1; k >= 0; k--) {
+      GMR_LANES
+        if (lane == k) s_xs()[6 + k] = L.rhs * L.dinv;
+      GMR_END
+      GMR_LANES
+        const R x = s_xs()[6 + k];
+        const R* lk = s_L() + gmr_loff(k);
+        if (lane < k) L.rhs -= lk[GMR_LC + lane] * x;
+        if (lane < 6) L.tmp -= lk[lane] * x;
+      GMR_END
     }
     GMR_LANES
       if (lane < 6) s_xs()[lane] = L.tmp;   // zf = yf - A'^T x_h
@@ -813,7 +839,7 @@ struct WarpSolver {
           R* o = s_L() + gmr_loff(lane);
           const R x = lp(LP_X, lane);
           GMR_UNROLL
-          for (int j = 0; j < GMR_NH; j++) if (j < lane) o[6 + j] = L.row[j] * x;
+          for (int j = 0; j < GMR_NH; j++) if (j < lane) o[GMR_LC + j] = L.row[j] * x;
         }
       GMR_END
       GMR_LANES
@@ -825,7 +851,7 @@ struct WarpSolver {
             for (int f = 0; f < 6; f++) g += L.a[f] * s_xs()[f];
             GMR_UNROLL
             for (int j = 0; j < GMR_NH; j++) if (j < lane) g += L.row[j] * s_xs()[6 + j];
-            for (int i = lane + 1; i < dm.nh; i++) g += s_L()[gmr_loff(i) + 6 + lane];
+            for (int i = lane + 1; i < dm.nh; i++) g += s_L()[gmr_loff(i) + GMR_LC + lane];
             lam = ((pin_lo >> lane) & 1u) ? g : -g;
           }
           s_red()[lane] = lam;

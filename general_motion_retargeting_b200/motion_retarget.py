@@ -349,7 +349,8 @@ class GeneralMotionRetargeting:
                 if heights is None:
                     d_ratio = torch.full((Cn,), self._ratio, dtype=torch.float32, device=dev)
                 else:
-                    d_ratio = (torch.as_tensor(heights, device=dev).to(torch.float32) / float(self._cfg.human_height_assumption)).contiguous()
+                    # float32(float64(height) / assumption): one definition for every entry point
+                    d_ratio = (torch.as_tensor(heights, device=dev).to(torch.float64) / float(self._cfg.human_height_assumption)).to(torch.float32).contiguous()
                 d_init = None if qpos_init is None else torch.as_tensor(qpos_init, device=dev).to(dt).contiguous()
                 d_q = torch.empty((Cn, T, nq), dtype=dt, device=dev)
                 d_it = torch.zeros((Cn, T, 2), dtype=torch.int32, device=dev) if return_info else None
@@ -371,7 +372,7 @@ class GeneralMotionRetargeting:
         if heights is None:
             a_ratio = np.full((Cn,), self._ratio, np.float32)
         else:
-            a_ratio = np.ascontiguousarray(np.asarray(heights, np.float32) / np.float32(self._cfg.human_height_assumption), np.float32)
+            a_ratio = np.ascontiguousarray(np.asarray(heights, np.float64) / float(self._cfg.human_height_assumption), np.float32)
         a_init = None if qpos_init is None else np.ascontiguousarray(qpos_init, np.float32)
         if out is not None:
             if out.dtype != np.float32 or tuple(out.shape) != (Cn, T, nq) or not out.flags.c_contiguous:

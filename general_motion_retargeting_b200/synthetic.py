@@ -91,7 +91,7 @@ class ClipBatch:
 
     def ratio(self, table: TaskTable) -> np.ndarray:
         """Per-clip height ratio exactly as the batched entry computes it (float32)."""
-        return (self.heights / np.float32(table.height_assumption)).astype(np.float32)
+        return (self.heights.astype(np.float64) / float(table.height_assumption)).astype(np.float32)
 
 
 def make_clips(robot: RobotModel, table: TaskTable, clip_ids: Sequence[int], T: int = 300,
@@ -189,7 +189,7 @@ def make_clips(robot: RobotModel, table: TaskTable, clip_ids: Sequence[int], T: 
         qh = _qmul(Rf, rot_off_c.expand_as(Rf))
         pp = pf - _qrot(Rf, pos_off.expand_as(pf))
         # inverse of scale_human_data with s = scale * ratio (ratio as the float32 the solver receives)
-        ratio = (heights32[c0:c1] / np.float32(table.height_assumption)).astype(np.float32).astype(np.float64)
+        ratio = (heights32[c0:c1].astype(np.float64) / float(table.height_assumption)).astype(np.float32).astype(np.float64)
         sc = scale[None, :] * tt(np.repeat(ratio, T))[:, None]                    # [N,nh]
         rootp = pp[:, table.root_idx] / sc[:, table.root_idx, None]               # [N,3]
         ph_ = (pp - pp[:, table.root_idx][:, None, :]) / sc[:, :, None] + rootp[:, None, :]

@@ -96,7 +96,7 @@ def test_known_answer_vectors(lib, torch_cuda):
     for key in sorted({k.rsplit(".", 1)[0] for k in g.files}):
         src, robot = key.split("_", 1)
         m, tt, _ = problem(src, robot)
-        ratio = (g[key + ".heights"] / np.float32(tt.height_assumption)).astype(np.float32)
+        ratio = (g[key + ".heights"].astype(np.float64) / float(tt.height_assumption)).astype(np.float32)
         for bits, tol in ((64, 1e-3), (32, 1e-3)):
             q, it, err = capi_run(lib, torch_cuda, m, tt, g[key + ".pos"], g[key + ".quat"], ratio, bits=bits)
             agree, dq_all, dq_clean = compare(q, it, g[key + ".qpos"], g[key + ".iters"])

@@ -198,7 +198,7 @@ def test_oracle_traces_fixture_is_reproducible(built):
     for key in sorted({k.rsplit(".", 1)[0] for k in g.files}):
         src, robot = key.split("_", 1)
         m, tt, _ = problem(src, robot)
-        ratio = (g[key + ".heights"] / np.float32(tt.height_assumption)).astype(np.float32)
+        ratio = (g[key + ".heights"].astype(np.float64) / float(tt.height_assumption)).astype(np.float32)
         q, it, err = native.retarget_batch(m, tt, g[key + ".pos"], g[key + ".quat"], ratio)
         np.testing.assert_array_equal(it, g[key + ".iters"])
         np.testing.assert_allclose(q, g[key + ".qpos"], atol=1e-9)
