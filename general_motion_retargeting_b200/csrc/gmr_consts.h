@@ -41,6 +41,9 @@ struct GmrConsts {
 struct GmrDims {
   int32_t nb, nh, nhum, nt, nlevel, nq, hroot, use1, use2, max_iter;
   uint32_t in1_mask, in2_mask, limited_mask, foot_mask;
+  // per-warp shared-memory layout for the launching precision (element offsets, see gmr_solver.cuh)
+  int32_t o_tg, o_in, o_xp, o_xq, o_u, warp_elems;
+  int16_t loff[GMR_NH + 2];   // packed factor-row offsets
 };
 template <typename R> struct GmrScal { R damping, lm, gain, tol, dt; };
 

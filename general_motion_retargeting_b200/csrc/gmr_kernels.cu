@@ -9,6 +9,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -16,6 +17,9 @@
 #include <vector>
 
 #include "gmr_solver.cuh"
+
+#define GMR_FLAG_INTERNAL_CONVOY 0x80000000u   // set by launch(), never by callers
+
 
 namespace {
 
@@ -68,9 +72,15 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
   stage_consts_tma(mc, gconsts, CB, bar);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
-  const int wel = gmr_warp_elems<R>(dm.nb, dm.nh, dm.nhum, dm.nt);
+  const int wel = dm.warp_elems;
   R* wsm = reinterpret_cast<R*>(smem + 16 + CB) + (size_t)warp * wel;
   WarpSolver<R> ws(*mc, dm, ks, wsm, lane);
+  ws.convoy = (flags & GMR_FLAG_INTERNAL_CONVOY) != 0;
+  ws.cta_active = reinterpret_cast<int*>(smem + 8);                  // second half of the mbarrier's 16-byte slot
+  if (ws.convoy) {
+    if (threadIdx.x == 0) *ws.cta_active = wpc;
+    __syncthreads();
+  }
   const int nq = dm.nq, nhum = dm.nhum;
   const int nw = gridDim.x * wpc;
   for (int c = warp * gridDim.x + blockIdx.x; c < C; c += nw) {
@@ -80,6 +90,7 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
                              iters ? iters + 2 * f0 : nullptr, err ? err + 2 * f0 : nullptr,
                              tg ? tg + f0 * nhum * 7 : nullptr, flags);
   }
+  ws.convoy_retire();
 }
 
 constexpr int MAXW_F32 = 28;   // 28 warps * 32 lanes * 72 registers = one SM's register file
@@ -94,7 +105,7 @@ struct GmrModel {
   GmrConsts<float>* d_f32 = nullptr;
   GmrConsts<double>* d_f64 = nullptr;
   GmrConsts<float> h_f32;
-  GmrDims dims{};
+  GmrDims dims32{}, dims64{};
   GmrScal<float> ks32{};
   GmrScal<double> ks64{};
   int wel32 = 0, wel64 = 0;      // per-warp shared-memory elements
@@ -129,10 +140,16 @@ template <> const GmrScal<float>& scal_of<float>(const GmrModel* m) { return m->
 template <> const GmrScal<double>& scal_of<double>(const GmrModel* m) { return m->ks64; }
 
 // warps per CTA: as many as fit (shared memory, register file), but no more than the clips need
+// CTAs (= independent convoys) per SM: two convoys overlap one's stragglers with the other's work
+inline int ctas_per_sm() {
+  static const int n = [] { const char* e = getenv("GMR_CTAS_PER_SM"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : (v > 7 ? 7 : v); }();
+  return n;
+}
 template <typename R> int pick_wpc(const GmrModel* m, int C) {
-  int wpc = max_warps<R>();
+  int wpc = max_warps<R>() / ctas_per_sm();
+  if (const char* cap = getenv("GMR_WPC_CAP")) { int c = atoi(cap); if (c >= 1 && c < wpc) wpc = c; }   // tuning knob
   while (wpc > 1 && smem_bytes<R>(m, wpc) > (size_t)m->max_smem) wpc--;
-  int need = (C + m->num_sms - 1) / m->num_sms;
+  int need = (C + m->num_sms * ctas_per_sm() - 1) / (m->num_sms * ctas_per_sm());
   if (need < 1) need = 1;
   if (need < wpc) wpc = need;
   return wpc;
@@ -152,8 +169,12 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
     configured = (const void*)kern;
   }
   int grid = (C + wpc - 1) / wpc;
-  if (grid > m->num_sms) grid = m->num_sms;
-  kern<<<grid, wpc * 32, smem, st>>>(m->dims, scal_of<R>(m), dc, pos, quat, ratio, C, T, qinit, qout, iters, err, tg, flags);
+  if (grid > m->num_sms * ctas_per_sm()) grid = m->num_sms * ctas_per_sm();
+  // convoy mode (see gmr_solver.cuh): worth it when an SM holds many warps; GMR_CONVOY=0/1 overrides
+  static const int cv_env = getenv("GMR_CONVOY") ? atoi(getenv("GMR_CONVOY")) : -1;
+  const bool convoy = cv_env >= 0 ? cv_env != 0 : wpc >= 8;
+  flags = (flags & 0xffffu) | (convoy ? GMR_FLAG_INTERNAL_CONVOY : 0u);
+  kern<<<grid, wpc * 32, smem, st>>>(sizeof(R) == 4 ? m->dims32 : m->dims64, scal_of<R>(m), dc, pos, quat, ratio, C, T, qinit, qout, iters, err, tg, flags);
   g_launches.fetch_add(1);
   CK(cudaGetLastError());
   return GMR_OK;
@@ -174,11 +195,12 @@ int gmr_model_create(const GmrModelDesc* desc, int device, GmrModel** out) {
   int rc = gmr_fill_consts<float>(desc, &m->h_f32, &why);
   if (rc == GMR_OK) rc = gmr_fill_consts<double>(desc, hd, &why);
   if (rc != GMR_OK) { delete hd; delete m; return set_err(rc, why ? why : "invalid model"); }
-  m->dims = gmr_dims_of(m->h_f32);
+  m->dims32 = gmr_dims_of(m->h_f32); gmr_dims_layout<float>(m->dims32);
+  m->dims64 = gmr_dims_of(m->h_f32); gmr_dims_layout<double>(m->dims64);
   m->ks32 = gmr_scal_of(m->h_f32);
   m->ks64 = gmr_scal_of(*hd);
-  m->wel32 = gmr_warp_elems<float>(m->dims.nb, m->dims.nh, m->dims.nhum, m->dims.nt);
-  m->wel64 = gmr_warp_elems<double>(m->dims.nb, m->dims.nh, m->dims.nhum, m->dims.nt);
+  m->wel32 = m->dims32.warp_elems;
+  m->wel64 = m->dims64.warp_elems;
   m->device = device;
   DeviceGuard g(device);
   cudaError_t e = g.ok ? cudaSuccess : cudaErrorInvalidDevice;

@@ -44,6 +44,12 @@
 #define GMR_END }
 #define GMR_UNROLL
 #define GMR_SYNC()
+// end the lane loop, broadcast per-lane register(s) of lane `src` to every lane, open a new lane loop
+#define GMR_BCAST1(src, f0) } { const R bc0 = lanes_[src].f0; for (int lane = 0; lane < 32; ++lane) { LaneRegs<R>& L = lanes_[lane]; (void)L;
+#define GMR_BCAST2(src, f0, f1) } { const R bc0 = lanes_[src].f0, bc1 = lanes_[src].f1; for (int lane = 0; lane < 32; ++lane) { LaneRegs<R>& L = lanes_[lane]; (void)L;
+#define GMR_END_BCAST } }
+#define GMR_END_BCAST_NOSYNC } }
+#define GMR_OWN_OFF (dm.loff[lane])
 #else
 #define GMR_FN __device__ __forceinline__
 #define GMR_HD __host__ __device__ inline
@@ -51,6 +57,12 @@
 #define GMR_END } __syncwarp();
 #define GMR_UNROLL _Pragma("unroll")
 #define GMR_SYNC() __syncwarp()
+// warp shuffles: no shared-memory round trip and no extra __syncwarp for a one-lane -> all-lanes hand-over
+#define GMR_BCAST1(src, f0) const R bc0 = __shfl_sync(0xffffffffu, L.f0, src);
+#define GMR_BCAST2(src, f0, f1) const R bc0 = __shfl_sync(0xffffffffu, L.f0, src), bc1 = __shfl_sync(0xffffffffu, L.f1, src);
+#define GMR_END_BCAST } __syncwarp();
+#define GMR_END_BCAST_NOSYNC }
+#define GMR_OWN_OFF (own_off_)
 #endif
 
 // ---- shared-memory layout of one warp's state (units: elements of R) -----------------------
@@ -88,6 +100,18 @@ template <typename R> GMR_HD int gmr_warp_elems(int nb, int nh, int nhum, int nt
   return GS_VAR + 8 * (nh > 0 ? nh : 1) + 8 * nhum + gmr_in_elems<R>(nhum) + gmr_pad4(3 * nb) + 4 * nb + gmr_pad4(u);
 }
 
+// fills the layout fields of `d` for precision R (host side, before launch)
+template <typename R> inline void gmr_dims_layout(GmrDims& d) {
+  int o = GS_VAR + 8 * (d.nh > 0 ? d.nh : 1);
+  d.o_tg = o; o += 8 * d.nhum;
+  d.o_in = o; o += gmr_in_elems<R>(d.nhum);
+  d.o_xp = o; o += gmr_pad4(3 * d.nb);
+  d.o_xq = o; o += 4 * d.nb;
+  d.o_u = o;
+  d.warp_elems = gmr_warp_elems<R>(d.nb, d.nh, d.nhum, d.nt);
+  for (int i = 0; i < GMR_NH + 2; i++) d.loff[i] = (int16_t)gmr_loff(i);
+}
+
 template <typename R> struct GmrEps;
 // `lie` is the reference's float64 threshold (mink get_epsilon(float64) = 10 eps) in BOTH precisions: the branch
 // decisions (Taylor vs closed form, the jlog = I shortcut) must follow the float64 reference, not the kernel's dtype.
@@ -99,23 +123,54 @@ template <> struct GmrEps<double> { static constexpr double lie = 2.220446049250
 template <typename R> struct LaneRegs {
   R a[6];          // base (floating joint) columns of this hinge's row of H, then of L
   R row[GMR_NH];   // hinge columns j <= lane
-  R rhs, dinv, tmp;
+  R rhs, dinv, tmp, zf;
 };
 
 // ---- tiny math helpers ----------------------------------------------------------------------
 template <typename R> GMR_FN R g_sqrt(R x) { return sqrt(x); }
 template <typename R> GMR_FN R g_atan2(R y, R x) { return atan2(y, x); }
 template <typename R> GMR_FN R g_abs(R x) { return fabs(x); }
-template <typename R> GMR_FN void g_sincos(R x, R* s, R* c) {
+template <typename R> GMR_FN R g_rsqrt(R x) {
 #ifdef GMR_EMULATE
-  *s = std::sin(x); *c = std::cos(x);
+  return R(1) / std::sqrt(x);
 #else
-  sincos(x, s, c);
+  return rsqrt(x);
 #endif
 }
+// sin/cos by quadrant reduction (x = k pi/2 + r, |r| <= pi/4) and minimax-free Taylor polynomials:
+// hinge half-angles and IK rotation steps are a few radians at most, so a two-constant Cody-Waite
+// reduction is exact enough (|x| < 1e4) and the whole thing is ~35 straight FMAs instead of the
+// library routine with its large-argument path.  Error < 1 ulp-ish of the working precision.
+template <typename R> GMR_FN void g_sincos(R x, R* s, R* c) {
+  const R k = rint(x * R(0.63661977236758134308));
+  R r = fma(-k, R(1.57079632679489655800e+00), x);
+  r = fma(-k, R(6.12323399573676603587e-17), r);
+  const R r2 = r * r;
+  R sp, cp;
+  if (sizeof(R) == 8) {
+    sp = fma(r2, R(-7.6471637318198164759e-13), R(1.6059043836821614599e-10));
+    sp = fma(r2, sp, R(-2.5052108385441718775e-08)); sp = fma(r2, sp, R(2.7557319223985890653e-06));
+    sp = fma(r2, sp, R(-1.9841269841269841270e-04)); sp = fma(r2, sp, R(8.3333333333333333333e-03));
+    sp = fma(r2, sp, R(-1.6666666666666666667e-01));
+    cp = fma(r2, R(4.7794773323873852974e-14), R(-1.1470745597729724714e-11));
+    cp = fma(r2, cp, R(2.0876756987868098979e-09)); cp = fma(r2, cp, R(-2.7557319223985890653e-07));
+    cp = fma(r2, cp, R(2.4801587301587301587e-05)); cp = fma(r2, cp, R(-1.3888888888888888889e-03));
+    cp = fma(r2, cp, R(4.1666666666666666667e-02)); cp = fma(r2, cp, R(-0.5));
+  } else {
+    sp = fma(r2, R(2.7557319223985890653e-06), R(-1.9841269841269841270e-04));
+    sp = fma(r2, sp, R(8.3333333333333333333e-03)); sp = fma(r2, sp, R(-1.6666666666666666667e-01));
+    cp = fma(r2, R(-2.7557319223985890653e-07), R(2.4801587301587301587e-05));
+    cp = fma(r2, cp, R(-1.3888888888888888889e-03)); cp = fma(r2, cp, R(4.1666666666666666667e-02)); cp = fma(r2, cp, R(-0.5));
+  }
+  const R sr = fma(r * r2, sp, r), cr = fma(r2, cp, R(1));
+  const int q = (int)k & 3;
+  const R ss = (q & 1) ? cr : sr, cc = (q & 1) ? sr : cr;
+  *s = (q & 2) ? -ss : ss;
+  *c = ((q + 1) & 2) ? -cc : cc;
+}
 #ifndef GMR_EMULATE
-template <> __device__ __forceinline__ void g_sincos<float>(float x, float* s, float* c) { sincosf(x, s, c); }
 template <> __device__ __forceinline__ float g_sqrt<float>(float x) { return sqrtf(x); }
+template <> __device__ __forceinline__ float g_rsqrt<float>(float x) { return rsqrtf(x); }
 template <> __device__ __forceinline__ float g_atan2<float>(float y, float x) { return atan2f(y, x); }
 template <> __device__ __forceinline__ float g_abs<float>(float x) { return fabsf(x); }
 #endif
@@ -167,9 +222,9 @@ template <typename R> GMR_FN void q_to_mat(const R* q, R* m) {
   m[6] = R(2) * (x * z - w * y); m[7] = R(2) * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
 }
 template <typename R> GMR_FN void q_normalize(R* q) {      // mju_normalize4
-  R n = g_sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-  if (n < R(1e-15)) { q[0] = R(1); q[1] = q[2] = q[3] = R(0); return; }
-  R inv = R(1) / n;
+  const R n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  if (n2 < R(1e-30)) { q[0] = R(1); q[1] = q[2] = q[3] = R(0); return; }
+  const R inv = g_rsqrt(n2);
   q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
 }
 // C = A * B (3x3 row-major)
@@ -209,43 +264,69 @@ struct WarpSolver {
   const GmrConsts<R>& mc;     // per-robot tables (shared memory on the GPU)
   const GmrDims& dm;          // sizes / masks (kernel parameter: constant bank)
   const GmrScal<R>& ks;       // solver knobs (kernel parameter)
-  R* sm;                      // this warp's shared-memory block
+#ifdef GMR_EMULATE
+  R* sm;                      // this warp's state block
+#else
+  // this warp's state block as a 32-bit byte offset into the dynamic shared window: keeps every
+  // access a plain LDS/STS [reg + imm] instead of 64-bit generic pointer arithmetic
+  uint32_t sm_off;
+  struct SmProxy {
+    uint32_t off;
+    __device__ __forceinline__ R* ptr() const { extern __shared__ __align__(128) unsigned char gmr_dyn_smem[]; return reinterpret_cast<R*>(gmr_dyn_smem + off); }
+    __device__ __forceinline__ R* operator+(int i) const { return ptr() + i; }
+    __device__ __forceinline__ R& operator[](int i) const { return ptr()[i]; }
+  };
+#endif
 #ifdef GMR_EMULATE
   LaneRegs<R> lanes_[32];
 #else
   LaneRegs<R> lanes_;
   int lane_;
+  int own_off_;                // offset of this lane's packed factor row
 #endif
   int stat_refactor;           // factorisations done (uniform)
+  bool convoy;                 // CTA-wide rendezvous before every factorisation (see convoy_arrive)
+  volatile int* cta_active;    // shared count of warps that still have clips (convoy mode)
   uint32_t warm_lo, warm_hi;   // working set carried from the previous solve (uniform)
 
   GMR_FN WarpSolver(const GmrConsts<R>& m, const GmrDims& d, const GmrScal<R>& k, R* smem
 #ifndef GMR_EMULATE
                     , int lane
 #endif
-                    ) : mc(m), dm(d), ks(k), sm(smem), stat_refactor(0), warm_lo(0), warm_hi(0) {
+                    ) : mc(m), dm(d), ks(k), stat_refactor(0), convoy(false), cta_active(nullptr), warm_lo(0), warm_hi(0) {
 #ifndef GMR_EMULATE
     lane_ = lane;
+    own_off_ = gmr_loff(lane);
+    extern __shared__ __align__(128) unsigned char gmr_dyn_smem[];
+    sm_off = (uint32_t)(reinterpret_cast<unsigned char*>(smem) - gmr_dyn_smem);
+#else
+    sm = smem;
 #endif
   }
 
+#ifndef GMR_EMULATE
+  #define sm (SmProxy{sm_off})
+#endif
   GMR_FN R* s_red() const { return sm + GS_RED; }
   GMR_FN R* s_xs() const { return sm + GS_XS; }
   GMR_FN R* s_root() const { return sm + GS_ROOT; }
   GMR_FN R* s_lf() const { return sm + GS_LF; }
   GMR_FN R* s_piv() const { return sm + GS_PIV; }
   GMR_FN R* s_bnd() const { return sm + GS_BND; }
-  GMR_FN R& lp(int slot, int lane) const { return sm[GS_LP + slot * 32 + lane]; }
+  GMR_FN R& lp(int slot, int lane) const { return *(sm + (GS_LP + slot * 32 + lane)); }
   GMR_FN R* s_q() const { return sm + GS_Q; }
   GMR_FN R* s_sd() const { return sm + GS_VAR; }
-  GMR_FN R* s_tg() const { return s_sd() + 8 * (dm.nh > 0 ? dm.nh : 1); }
-  GMR_FN float* s_in() const { return reinterpret_cast<float*>(s_tg() + 8 * dm.nhum); }
-  GMR_FN R* s_xp() const { return s_tg() + 8 * dm.nhum + gmr_in_elems<R>(dm.nhum); }
-  GMR_FN R* s_xq() const { return s_xp() + gmr_pad4(3 * dm.nb); }
-  GMR_FN R* s_U() const { return s_xq() + 4 * dm.nb; }
+  GMR_FN R* s_tg() const { return sm + dm.o_tg; }
+  GMR_FN float* s_in() const { return reinterpret_cast<float*>(sm + dm.o_in); }
+  GMR_FN R* s_xp() const { return sm + dm.o_xp; }
+  GMR_FN R* s_xq() const { return sm + dm.o_xq; }
+  GMR_FN R* s_U() const { return sm + dm.o_u; }
   GMR_FN R* s_sc() const { return s_U(); }      // half-angle sin/cos, live only inside fk()
   GMR_FN R* s_mt() const { return s_U(); }      // task inertias, dead once the rows are built
   GMR_FN R* s_L() const { return s_U(); }       // packed factor rows
+#ifndef GMR_EMULATE
+  #undef sm
+#endif
 
   // ------------------------------------------------------------------ configuration --------
   template <typename S> GMR_FN void set_qpos(const S* src) {
@@ -467,12 +548,21 @@ struct WarpSolver {
     GMR_END
   }
 
-  // unweighted error norm of the stage's tasks (error1()/error2(), motion_retarget.py:188-200)
+  // unweighted error norm of the stage's tasks (error1()/error2(), motion_retarget.py:188-200):
+  // lane t holds |e_t|^2 in s_red[t]; butterfly sum over the lanes of the stage's tasks
   GMR_FN R stage_error(int stage) const {
     const uint32_t m = stage == 0 ? dm.in1_mask : dm.in2_mask;
-    R s = R(0);
-    for (int t = 0; t < dm.nt; t++) if ((m >> t) & 1u) s += s_red()[t];
-    return g_sqrt(s);
+#ifdef GMR_EMULATE
+    R part[32];
+    for (int t = 0; t < 32; t++) part[t] = (t < dm.nt && ((m >> t) & 1u)) ? s_red()[t] : R(0);
+    for (int o = 16; o > 0; o >>= 1) for (int t = 0; t < 32; t++) if ((t & o) == 0) { const R a = part[t], b = part[t ^ o]; part[t] = part[t ^ o] = a + b; }
+    return g_sqrt(part[0]);
+#else
+    R v = (lane_ < dm.nt && ((m >> lane_) & 1u)) ? s_red()[lane_] : R(0);
+    GMR_UNROLL
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return g_sqrt(v);
+#endif
   }
 
   // ------------------------------------------------------------------ composites ------------
@@ -548,7 +638,7 @@ struct WarpSolver {
       GMR_LANES
         if (lane < dm.nh && ((pinned >> lane) & 1u)) {
           const R bv = s_bnd()[lane];
-          R* o = s_L() + gmr_loff(lane);
+          R* o = s_L() + GMR_OWN_OFF;
           GMR_UNROLL
           for (int g = 0; g < 6; g++) o[g] = L.a[g] * bv;
           GMR_UNROLL
@@ -569,7 +659,7 @@ struct WarpSolver {
             for (int j = 0; j < GMR_NH; j++) {
               if ((pinned >> j) & 1u) {
                 if (j < lane) { r -= L.row[j] * s_bnd()[j]; L.row[j] = R(0); }
-                else if (j > lane && j < dm.nh) r -= s_L()[gmr_loff(j) + GMR_LC + lane];
+                else if (j > lane && j < dm.nh) r -= s_L()[dm.loff[j] + GMR_LC + lane];
               }
             }
             L.rhs = r;
@@ -578,7 +668,7 @@ struct WarpSolver {
         // base right-hand side correction, gathered by lanes 0..5 into s_xs[0..5]
         if (lane < 6) {
           R r = R(0);
-          for (int j = 0; j < dm.nh; j++) if ((pinned >> j) & 1u) r += s_L()[gmr_loff(j) + lane];
+          for (int j = 0; j < dm.nh; j++) if ((pinned >> j) & 1u) r += s_L()[dm.loff[j] + lane];
           s_xs()[lane] = r;
         }
       GMR_END
@@ -610,20 +700,18 @@ struct WarpSolver {
             R s = A[gmr_sym6(j, i)];
             GMR_UNROLL
             for (int k = 0; k < j; k++) s -= lf[i * (i + 1) / 2 + k] * lf[j * (j + 1) / 2 + k];
-            if (i == j) lf[i * (i + 1) / 2 + i] = g_sqrt(s);
-            else lf[i * (i + 1) / 2 + j] = s / lf[j * (j + 1) / 2 + j];
+            if (i == j) lf[i * (i + 1) / 2 + i] = g_rsqrt(s);            // reciprocal diagonal 1 / L_ii
+            else lf[i * (i + 1) / 2 + j] = s * lf[j * (j + 1) / 2 + j];
           }
         }
-        // yf = Lf^-1 b ; store Lf with reciprocal diagonal
+        // yf = Lf^-1 b
         R y[6];
         GMR_UNROLL
         for (int i = 0; i < 6; i++) {
           R s = b[i];
           GMR_UNROLL
           for (int k = 0; k < i; k++) s -= lf[i * (i + 1) / 2 + k] * y[k];
-          const R di = R(1) / lf[i * (i + 1) / 2 + i];
-          lf[i * (i + 1) / 2 + i] = di;
-          y[i] = s * di;
+          y[i] = s * lf[i * (i + 1) / 2 + i];
         }
         R* o = s_lf();
         GMR_UNROLL
@@ -650,7 +738,7 @@ struct WarpSolver {
         }
         L.rhs = r;
         // initialise this lane's packed row: a', two pad zeros, zeros over its hinge columns, -1 on the diagonal
-        R* o = s_L() + gmr_loff(lane);
+        R* o = s_L() + GMR_OWN_OFF;
         GMR_UNROLL
         for (int g = 0; g < 6; g++) o[g] = L.a[g];
         o[6] = R(0); o[7] = R(0);
@@ -658,47 +746,49 @@ struct WarpSolver {
         for (int j = 0; j < nc; j++) o[GMR_LC + j] = (j == lane) ? R(-1) : R(0);
       }
     GMR_END
-    // hinge block, column by column.  Blocks of 4 pivots: the outer loop is ROLLED (the code of one
-    // block is reused, which keeps the instruction footprint small), registers are indexed
-    // statically inside a block and the only block-dependent register access — storing the new
-    // column into row[4b+e] — goes through a switch.
+    // hinge block, column by column.  Pivots are taken in blocks of 4: the outer loop over blocks is
+    // ROLLED (one copy of the block in the instruction stream — the kernel is instruction-supply
+    // bound), inside a block the registers are indexed statically and the only
+    // block-dependent register access — storing the new column into row[4b+e] — goes through an
+    // 8-way switch.  Lane k hands 1/L_kk and y_k to the other lanes with two shuffles; one
+    // __syncwarp per pivot orders the shared-memory row writes.
     const int nblk = (dm.nh + 3) >> 2;
     for (int b = 0; b < nblk; b++) {
+      const int nchunk = 3 + b;                         // pivot row length = 4 * (3 + b)
       GMR_UNROLL
       for (int e = 0; e < 4; e++) {
         const int k = 4 * b + e;
         if (k < dm.nh) {
           GMR_LANES
             if (lane >= k && lane < dm.nh) {
-              const R* lk = s_L() + gmr_loff(k);
-              R s = R(0);
+              const R* lk = s_L() + dm.loff[k];
+              R s0 = R(0), s1 = R(0);
               GMR_UNROLL
               for (int c = 0; c < 2 + GMR_NH / 4; c++) {
-                if (c < 3 + b) {                      // pivot row length = 4 * (3 + b)
+                if (c < nchunk) {
                   R v[4]; g_ld4(lk + 4 * c, v);
                   GMR_UNROLL
                   for (int u = 0; u < 4; u++) {
                     const int p = 4 * c + u;
-                    if (p < 6) s += L.a[p < 6 ? p : 0] * v[u];
-                    else if (p >= GMR_LC) s += L.row[(p >= GMR_LC && p < GMR_LC + GMR_NH) ? p - GMR_LC : 0] * v[u];
+                    if (p < 6) { if (u & 1) s1 += L.a[p < 6 ? p : 0] * v[u]; else s0 += L.a[p < 6 ? p : 0] * v[u]; }
+                    else if (p >= GMR_LC) {
+                      const int m = (p >= GMR_LC && p < GMR_LC + GMR_NH) ? p - GMR_LC : 0;
+                      if (u & 1) s1 += L.row[m] * v[u]; else s0 += L.row[m] * v[u];
+                    }
                   }
                 }
               }
-              s = -s;                                  // = H_ik - sum_{m<k} L_im L_km (base columns included)
+              const R s = -(s0 + s1);                    // = H_ik - sum_{m<k} L_im L_km (base columns included)
               if (lane == k) {
-                const R d = g_sqrt(s), di = R(1) / d;
-                L.dinv = di;
-                const R y = L.rhs * di;
-                L.rhs = y;
-                s_piv()[0] = di; s_piv()[1] = y;
+                const R di = g_rsqrt(s);
+                L.dinv = di; L.rhs *= di; L.tmp = di;
               } else {
                 L.tmp = s;
               }
             }
-          GMR_END
-          GMR_LANES
+          GMR_BCAST2(k, tmp, rhs)
             if (lane > k && lane < dm.nh) {
-              const R l = L.tmp * s_piv()[0];
+              const R l = L.tmp * bc0;
               switch (b) {
                 case 0: L.row[0 + e] = l; break;
                 case 1: L.row[4 + e] = l; break;
@@ -709,30 +799,28 @@ struct WarpSolver {
                 case 6: L.row[24 + e] = l; break;
                 default: L.row[28 + e] = l; break;
               }
-              s_L()[gmr_loff(lane) + GMR_LC + k] = l;
-              L.rhs -= l * s_piv()[1];
+              s_L()[GMR_OWN_OFF + GMR_LC + k] = l;
+              L.rhs -= l * bc1;
             }
-          GMR_END
+          GMR_END_BCAST
         }
       }
     }
     // back substitution: hinges from the last to the first, lanes 0..5 also accumulate A'^T x
     GMR_LANES
-      L.tmp = (lane < 6) ? s_lf()[21 + lane] : R(0);      // zf accumulators (lanes 0..5)
+      L.zf = (lane < 6) ? s_lf()[21 + lane] : R(0);      // zf accumulators (lanes 0..5)
     GMR_END
     for (int k = dm.nh - 1; k >= 0; k--) {
       GMR_LANES
-        if (lane == k) s_xs()[6 + k] = L.rhs * L.dinv;
-      GMR_END
-      GMR_LANES
-        const R x = s_xs()[6 + k];
-        const R* lk = s_L() + gmr_loff(k);
-        if (lane < k) L.rhs -= lk[GMR_LC + lane] * x;
-        if (lane < 6) L.tmp -= lk[lane] * x;
-      GMR_END
+        if (lane == k) { L.tmp = L.rhs * L.dinv; s_xs()[6 + k] = L.tmp; }
+      GMR_BCAST1(k, tmp)
+        const R* lk = s_L() + dm.loff[k];
+        if (lane < k) L.rhs -= lk[GMR_LC + lane] * bc0;
+        if (lane < 6) L.zf -= lk[lane] * bc0;
+      GMR_END_BCAST_NOSYNC
     }
     GMR_LANES
-      if (lane < 6) s_xs()[lane] = L.tmp;   // zf = yf - A'^T x_h
+      if (lane < 6) s_xs()[lane] = L.zf;   // zf = yf - A'^T x_h
     GMR_END
     GMR_LANES
       if (lane == 0) {                                     // x_f = Lf^-T zf
@@ -784,6 +872,7 @@ struct WarpSolver {
           if (lane < dm.nh) s_bnd()[lane] = ((pin_hi >> lane) & 1u) ? bound_hi(lane) : bound_lo(lane);
         GMR_END
       }
+      if (!check) convoy_arrive();
       build_rows(check ? 0u : pinned);
       if (!check) {
         factor_solve(pinned);
@@ -836,7 +925,7 @@ struct WarpSolver {
       // CHECK pass: g = H x + c on the original rows (just rebuilt); x is in s_xs
       GMR_LANES
         if (lane < dm.nh) {
-          R* o = s_L() + gmr_loff(lane);
+          R* o = s_L() + GMR_OWN_OFF;
           const R x = lp(LP_X, lane);
           GMR_UNROLL
           for (int j = 0; j < GMR_NH; j++) if (j < lane) o[GMR_LC + j] = L.row[j] * x;
@@ -851,7 +940,7 @@ struct WarpSolver {
             for (int f = 0; f < 6; f++) g += L.a[f] * s_xs()[f];
             GMR_UNROLL
             for (int j = 0; j < GMR_NH; j++) if (j < lane) g += L.row[j] * s_xs()[6 + j];
-            for (int i = lane + 1; i < dm.nh; i++) g += s_L()[gmr_loff(i) + GMR_LC + lane];
+            for (int i = lane + 1; i < dm.nh; i++) g += s_L()[dm.loff[i] + GMR_LC + lane];
             lam = ((pin_lo >> lane) & 1u) ? g : -g;
           }
           s_red()[lane] = lam;
@@ -939,6 +1028,31 @@ struct WarpSolver {
 #ifndef GMR_EMULATE
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
+#endif
+  }
+
+  // ------------------------------------------------------------------ convoy -----------------
+  // All warps of a CTA run the same ~16k-instruction solve on different clips.  Left alone they
+  // drift apart, every warp streams its own copy of the code through the instruction caches and
+  // the SM starves (ncu: stall "no instruction" ~10 of ~20 warp-cycles per issue; the hot path
+  // is ~75 KB against a 32 KB instruction cache).  One CTA-wide rendezvous per factorisation
+  // keeps the warps inside the same stretch of code, so a fetched line serves all of them.
+  // Everything between two rendezvous is the same amount of work for every warp (one
+  // factorisation + the bookkeeping up to the next one); extra active-set passes simply take
+  // extra rounds.  Warps that ran out of clips keep arriving until the CTA is done.
+  GMR_FN void convoy_arrive() {
+#ifndef GMR_EMULATE
+    if (convoy) __syncthreads();
+#endif
+  }
+  GMR_FN void convoy_retire() {
+#ifndef GMR_EMULATE
+    if (!convoy) return;
+    if (lane_ == 0) atomicSub((int*)cta_active, 1);
+    for (;;) {
+      __syncthreads();
+      if (*cta_active <= 0) break;
+    }
 #endif
   }
 

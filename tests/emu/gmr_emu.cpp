@@ -17,9 +17,10 @@ static int run(const GmrModelDesc* d, const float* pos, const float* quat, const
   const char* why = nullptr;
   int rc = gmr_fill_consts<R>(d, mc, &why);
   if (rc != GMR_OK) { delete mc; return rc; }
-  const GmrDims dims = gmr_dims_of(*mc);
+  GmrDims dims = gmr_dims_of(*mc);
+  gmr_dims_layout<R>(dims);
   const GmrScal<R> ks = gmr_scal_of(*mc);
-  const int wel = gmr_warp_elems<R>(dims.nb, dims.nh, dims.nhum, dims.nt);
+  const int wel = dims.warp_elems;
   if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
   if (nthreads > C) nthreads = C > 0 ? C : 1;
   std::atomic<int> next{0};

@@ -41,12 +41,14 @@ def emu_retarget_batch(robot, table, pos, quat, ratio, bits=64, flags=0, qpos_in
     return qpos, iters, err, tg, refac.value
 
 
-def compare(q, it, q_ref, it_ref):
-    """(agreement rate of iteration counts, max|dq| over all frames, max|dq| over frames whose
-    counts agree and that follow an agreeing frame)."""
+def compare(q, it, q_ref, it_ref, settle=5):
+    """(agreement rate of the per-frame iteration counts, max|dq| over all frames, max|dq| over
+    "clean" frames = frames whose counts agree and that are at least `settle` frames after the last
+    disagreement of their clip: a different count is a different number of IK steps, whose effect
+    takes a few warm-started frames to die out)."""
     same = (it == it_ref).all(-1)
     dq = np.abs(q - q_ref).max(-1)
-    prev_same = np.ones_like(same)
-    prev_same[:, 1:] = same[:, :-1]
-    clean = same & prev_same
+    clean = same.copy()
+    for s in range(1, settle + 1):
+        clean[:, s:] &= same[:, :-s]
     return float(same.mean()), float(dq.max()), float(dq[clean].max()) if clean.any() else 0.0
