@@ -250,6 +250,9 @@ int gmr_retarget_batch(GmrModel* m, const float* pos, const float* quat, const f
   if ((reinterpret_cast<uintptr_t>(quat) & 15u) != 0) return set_err(GMR_EINVAL, "quat must be 16-byte aligned");
   DeviceGuard g(m->device);
   if (!g.ok) return set_err(GMR_ECUDA, "cannot select the model's device");
+  if (flags & GMR_FLAG_COMPUTE_F64)
+    return launch<double, float, MAXW_F64>(m, m->d_f64, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out,
+                                           targets_out, flags, (cudaStream_t)cuda_stream);
   return launch<float, float, MAXW_F32>(m, m->d_f32, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out,
                                         targets_out, flags, (cudaStream_t)cuda_stream);
 }
@@ -285,7 +288,7 @@ int gmr_retarget_batch_host(GmrModel* m, const float* pos, const float* quat, co
                b_ratio = ratio ? 4 : 0, b_init = qpos_init ? (size_t)nq * 4 : 0;
   const size_t per_clip = b_pos + b_quat + b_q + b_it + b_err + b_ratio + b_init;
   // chunks of whole "waves" (one clip per resident warp) so that every chunk fills the GPU
-  const int wave = m->num_sms * pick_wpc<float>(m, C);
+  const int wave = m->num_sms * ((flags & GMR_FLAG_COMPUTE_F64) ? pick_wpc<double>(m, C) : pick_wpc<float>(m, C));
   int chunk = C;
   if (C >= 4 * wave) chunk = ((C / 4 + wave - 1) / wave) * wave;            // >= 4 chunks when there is enough work
   const size_t budget = (size_t)8 << 30;
@@ -312,11 +315,18 @@ int gmr_retarget_batch_host(GmrModel* m, const float* pos, const float* quat, co
     CK(cudaMemcpyAsync(d + o_quat, quat + (size_t)c0 * T * nh * 4, b_quat * n, cudaMemcpyHostToDevice, st));
     if (ratio) CK(cudaMemcpyAsync(d + o_ratio, ratio + c0, b_ratio * n, cudaMemcpyHostToDevice, st));
     if (qpos_init) CK(cudaMemcpyAsync(d + o_init, qpos_init + (size_t)c0 * nq, b_init * n, cudaMemcpyHostToDevice, st));
-    rc = launch<float, float, MAXW_F32>(m, m->d_f32, (const float*)(d + o_pos), (const float*)(d + o_quat),
-                                        ratio ? (const float*)(d + o_ratio) : nullptr, n, T,
-                                        qpos_init ? (const float*)(d + o_init) : nullptr, (float*)(d + o_q),
-                                        iters_out ? (int32_t*)(d + o_it) : nullptr, err_out ? (float*)(d + o_err) : nullptr,
-                                        nullptr, flags, st);
+    if (flags & GMR_FLAG_COMPUTE_F64)
+      rc = launch<double, float, MAXW_F64>(m, m->d_f64, (const float*)(d + o_pos), (const float*)(d + o_quat),
+                                           ratio ? (const float*)(d + o_ratio) : nullptr, n, T,
+                                           qpos_init ? (const float*)(d + o_init) : nullptr, (float*)(d + o_q),
+                                           iters_out ? (int32_t*)(d + o_it) : nullptr, err_out ? (float*)(d + o_err) : nullptr,
+                                           nullptr, flags, st);
+    else
+      rc = launch<float, float, MAXW_F32>(m, m->d_f32, (const float*)(d + o_pos), (const float*)(d + o_quat),
+                                          ratio ? (const float*)(d + o_ratio) : nullptr, n, T,
+                                          qpos_init ? (const float*)(d + o_init) : nullptr, (float*)(d + o_q),
+                                          iters_out ? (int32_t*)(d + o_it) : nullptr, err_out ? (float*)(d + o_err) : nullptr,
+                                          nullptr, flags, st);
     if (rc != GMR_OK) break;
     CK(cudaMemcpyAsync(qpos_out + (size_t)c0 * T * nq, d + o_q, b_q * n, cudaMemcpyDeviceToHost, st));
     if (iters_out) CK(cudaMemcpyAsync(iters_out + (size_t)c0 * T * 2, d + o_it, b_it * n, cudaMemcpyDeviceToHost, st));

@@ -31,6 +31,7 @@ extern "C" {
 
 /* flags for gmr_retarget_batch */
 #define GMR_FLAG_OFFSET_TO_GROUND  1u  /* retarget(..., offset_to_ground=True), motion_retarget.py:122-123,252-270 */
+#define GMR_FLAG_COMPUTE_F64       4u  /* gmr_retarget_batch / _host: float32 buffers, float64 arithmetic in the kernel */
 #define GMR_FLAG_NO_SOLVE          2u  /* update_targets()/error1()/error2() only: targets_out and err_out at the given
                                          configuration, qpos_out = qpos_init, no IK step (motion_retarget.py:117-136,188-200) */
 

@@ -41,14 +41,13 @@ def emu_retarget_batch(robot, table, pos, quat, ratio, bits=64, flags=0, qpos_in
     return qpos, iters, err, tg, refac.value
 
 
-def compare(q, it, q_ref, it_ref, settle=5):
+def compare(q, it, q_ref, it_ref):
     """(agreement rate of the per-frame iteration counts, max|dq| over all frames, max|dq| over
-    "clean" frames = frames whose counts agree and that are at least `settle` frames after the last
-    disagreement of their clip: a different count is a different number of IK steps, whose effect
-    takes a few warm-started frames to die out)."""
+    frames with an identical iteration history = frames of a clip up to and including the last
+    frame before its first count mismatch).  A different count is a different number of IK
+    steps; its effect persists through the warm start for as long as the clip takes to
+    re-converge, so frames after a mismatch are not 'identical inputs and iteration counts'."""
     same = (it == it_ref).all(-1)
     dq = np.abs(q - q_ref).max(-1)
-    clean = same.copy()
-    for s in range(1, settle + 1):
-        clean[:, s:] &= same[:, :-s]
+    clean = np.logical_and.accumulate(same, axis=1)
     return float(same.mean()), float(dq.max()), float(dq[clean].max()) if clean.any() else 0.0
