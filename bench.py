@@ -146,7 +146,7 @@ def main_reference(args):
     from general_motion_retargeting_b200.synthetic import make_clips
     robot, table = load_problem(args)
     cores = os.cpu_count() or 1
-    sample = max(2 * cores, 16)
+    sample = max(8 * cores, 64)          # enough clips per thread that the tail does not dominate
     clips = make_clips(robot, table, range(sample), T=args.frames, src_human=args.src)
     for _ in range(max(args.warmup, 0)):
         cpu_reference_run(robot, table, clips)
