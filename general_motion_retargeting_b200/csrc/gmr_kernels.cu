@@ -65,7 +65,8 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
                     const GmrConsts<R>* __restrict__ gconsts, const float* __restrict__ pos, const float* __restrict__ quat,
                     const float* __restrict__ ratio, int C, int T, const IO* __restrict__ qinit, IO* __restrict__ qout,
                     int32_t* __restrict__ iters, IO* __restrict__ err, IO* __restrict__ tg, uint32_t flags) {
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char gmr_dyn_smem[];
+  unsigned char* const smem = gmr_dyn_smem;
   constexpr int CB = consts_bytes<R>();
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);                 // 16 bytes reserved for the mbarrier
   GmrConsts<R>* mc = reinterpret_cast<GmrConsts<R>*>(smem + 16);
@@ -73,8 +74,7 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
   const int wel = dm.warp_elems;
-  R* wsm = reinterpret_cast<R*>(smem + 16 + CB) + (size_t)warp * wel;
-  WarpSolver<R> ws(*mc, dm, ks, wsm, lane);
+  WarpSolver<R> ws(*mc, dm, ks, (uint32_t)(16 + CB) + (uint32_t)warp * (uint32_t)wel * (uint32_t)sizeof(R), lane);
   ws.convoy = (flags & GMR_FLAG_INTERNAL_CONVOY) != 0;
   ws.cta_active = reinterpret_cast<int*>(smem + 8);                  // second half of the mbarrier's 16-byte slot
   if (ws.convoy) {

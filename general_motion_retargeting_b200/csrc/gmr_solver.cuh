@@ -289,16 +289,17 @@ struct WarpSolver {
   volatile int* cta_active;    // shared count of warps that still have clips (convoy mode)
   uint32_t warm_lo, warm_hi;   // working set carried from the previous solve (uniform)
 
-  GMR_FN WarpSolver(const GmrConsts<R>& m, const GmrDims& d, const GmrScal<R>& k, R* smem
-#ifndef GMR_EMULATE
-                    , int lane
+#ifdef GMR_EMULATE
+  GMR_FN WarpSolver(const GmrConsts<R>& m, const GmrDims& d, const GmrScal<R>& k, R* smem)
+#else
+  // smem_byte_off: offset of this warp's state block from the start of the dynamic shared window
+  GMR_FN WarpSolver(const GmrConsts<R>& m, const GmrDims& d, const GmrScal<R>& k, uint32_t smem_byte_off, int lane)
 #endif
-                    ) : mc(m), dm(d), ks(k), stat_refactor(0), convoy(false), cta_active(nullptr), warm_lo(0), warm_hi(0) {
+                     : mc(m), dm(d), ks(k), stat_refactor(0), convoy(false), cta_active(nullptr), warm_lo(0), warm_hi(0) {
 #ifndef GMR_EMULATE
     lane_ = lane;
     own_off_ = gmr_loff(lane);
-    extern __shared__ __align__(128) unsigned char gmr_dyn_smem[];
-    sm_off = (uint32_t)(reinterpret_cast<unsigned char*>(smem) - gmr_dyn_smem);
+    sm_off = smem_byte_off;
 #else
     sm = smem;
 #endif
