@@ -86,18 +86,24 @@ enum {
   GS_ROOT = 72,             // [28] whole-tree composite: M(21) g(6) mu
   GS_LF = 100,              // [28] base 6x6 factor (21, reciprocal diagonal) + y_base(6)
   GS_PIV = 128,             // [4]
-  GS_BND = 132,             // [32] bound value of pinned hinges
-  GS_LP = 164,              // [9][32] lane-private slots
-  GS_Q = 164 + 9 * 32,      // [40] qpos
-  GS_VAR = 164 + 9 * 32 + 40
+  GS_RQ = 132,              // [4] normalised root quaternion of the last FK
+  GS_BND = 136,             // [32] bound value of pinned hinges
+  GS_LP = 168,              // [9][32] lane-private slots
+  GS_Q = 168 + 9 * 32,      // [40] qpos
+  GS_VAR = 168 + 9 * 32 + 40
 };
 enum { LP_F = 0, LP_DIAG = 6, LP_CI = 7, LP_X = 8 };
 
 template <typename R> GMR_HD int gmr_in_elems(int nhum) { return gmr_pad4((int)((8 * nhum * sizeof(float) + sizeof(R) - 1) / sizeof(R))); }
-// variable part: sd[8nh] tg[8nhum] in[staged floats] xp[pad4(3nb)] xq[4nb] U[max(28nt, loff(nh), 64)]
+// variable part: sd[8nh] tg[8nhum] in[staged floats] U, where the union U holds
+//   [ mt: task inertias, max(28 nt, 64) | xp: pad4(3 nb) | xq: 4 nb ]   while FK / task evaluation are live, and
+//   [ packed factor rows, loff(nh) ]                                        from the factorisation to the next FK.
+// (body poses are dead once the composites are built; integrate() takes the root quaternion from GS_RQ.)
+GMR_HD constexpr int gmr_mt_elems(int nt) { return gmr_pad4(28 * nt > 64 ? 28 * nt : 64); }
 template <typename R> GMR_HD int gmr_warp_elems(int nb, int nh, int nhum, int nt) {
-  int u = 28 * nt; if (gmr_loff(nh) > u) u = gmr_loff(nh); if (u < 64) u = 64;
-  return GS_VAR + 8 * (nh > 0 ? nh : 1) + 8 * nhum + gmr_in_elems<R>(nhum) + gmr_pad4(3 * nb) + 4 * nb + gmr_pad4(u);
+  int u = gmr_mt_elems(nt) + gmr_pad4(3 * nb) + 4 * nb;
+  if (gmr_loff(nh) > u) u = gmr_loff(nh);
+  return GS_VAR + 8 * (nh > 0 ? nh : 1) + 8 * nhum + gmr_in_elems<R>(nhum) + gmr_pad4(u);
 }
 
 // fills the layout fields of `d` for precision R (host side, before launch)
@@ -105,9 +111,9 @@ template <typename R> inline void gmr_dims_layout(GmrDims& d) {
   int o = GS_VAR + 8 * (d.nh > 0 ? d.nh : 1);
   d.o_tg = o; o += 8 * d.nhum;
   d.o_in = o; o += gmr_in_elems<R>(d.nhum);
-  d.o_xp = o; o += gmr_pad4(3 * d.nb);
-  d.o_xq = o; o += 4 * d.nb;
   d.o_u = o;
+  d.o_xp = o + gmr_mt_elems(d.nt);
+  d.o_xq = d.o_xp + gmr_pad4(3 * d.nb);
   d.warp_elems = gmr_warp_elems<R>(d.nb, d.nh, d.nhum, d.nt);
   for (int i = 0; i < GMR_NH + 2; i++) d.loff[i] = (int16_t)gmr_loff(i);
 }
@@ -314,6 +320,7 @@ struct WarpSolver {
   GMR_FN R* s_lf() const { return sm + GS_LF; }
   GMR_FN R* s_piv() const { return sm + GS_PIV; }
   GMR_FN R* s_bnd() const { return sm + GS_BND; }
+  GMR_FN R* s_rq() const { return sm + GS_RQ; }
   GMR_FN R& lp(int slot, int lane) const { return *(sm + (GS_LP + slot * 32 + lane)); }
   GMR_FN R* s_q() const { return sm + GS_Q; }
   GMR_FN R* s_sd() const { return sm + GS_VAR; }
@@ -349,6 +356,8 @@ struct WarpSolver {
         q_normalize(q);
         s_xq()[0] = q[0]; s_xq()[1] = q[1]; s_xq()[2] = q[2]; s_xq()[3] = q[3];
         s_xp()[0] = R(0); s_xp()[1] = R(0); s_xp()[2] = R(0);
+        R* rq = s_rq();
+        rq[0] = q[0]; rq[1] = q[1]; rq[2] = q[2]; rq[3] = q[3];
       }
     GMR_END
     for (int l = 1; l < dm.nlevel; l++) {
@@ -979,7 +988,7 @@ struct WarpSolver {
       if (lane == 0) {
         GMR_UNROLL
         for (int i = 0; i < 3; i++) { const R v = s_xs()[i] / dt; s_q()[i] += dt * v; }
-        R q[4]; g_ld4(s_xq(), q);                                  // normalised root quaternion
+        R q[4]; g_ld4(s_rq(), q);                              // normalised root quaternion (s_xq is overwritten by the factor rows)
         R ww[3] = {s_xs()[3], s_xs()[4], s_xs()[5]}, wl[3];
         q_rot_inv(q, ww, wl);
         R v[3] = {wl[0] / dt, wl[1] / dt, wl[2] / dt};
