@@ -625,11 +625,16 @@ struct WarpSolver {
   // unit twists at the root origin, world-aligned), rhs = -c_i.  With pins: pinned lanes become
   // identity rows with rhs = bound, free lanes move the pinned columns to the right-hand side.
   GMR_FN void build_rows(uint32_t pinned) {
+    // every lane defines ALL of its row registers here (lanes >= nh get an identity row): a full
+    // redefinition is what tells the compiler that row[] is dead between two solves, so the
+    // phases in between (FK, task evaluation, composites) have the whole register file
     GMR_LANES
-      if (lane < dm.nh) {
-        const uint32_t am = mc.anc_mask[lane];
-        const R f0 = lp(LP_F, lane), f1 = lp(LP_F + 1, lane), f2 = lp(LP_F + 2, lane), f3 = lp(LP_F + 3, lane), f4 = lp(LP_F + 4, lane), f5 = lp(LP_F + 5, lane);
-        const R dg = lp(LP_DIAG, lane);
+      {
+        const bool act = lane < dm.nh;
+        const uint32_t am = act ? mc.anc_mask[lane] : 0u;
+        const R f0 = act ? lp(LP_F, lane) : R(0), f1 = act ? lp(LP_F + 1, lane) : R(0), f2 = act ? lp(LP_F + 2, lane) : R(0),
+                f3 = act ? lp(LP_F + 3, lane) : R(0), f4 = act ? lp(LP_F + 4, lane) : R(0), f5 = act ? lp(LP_F + 5, lane) : R(0);
+        const R dg = act ? lp(LP_DIAG, lane) : R(1);
         GMR_UNROLL
         for (int j = 0; j < GMR_NH; j++) {
           R v = R(0);
@@ -640,7 +645,8 @@ struct WarpSolver {
           L.row[j] = (j == lane) ? dg : v;
         }
         L.a[0] = f0; L.a[1] = f1; L.a[2] = f2; L.a[3] = f3; L.a[4] = f4; L.a[5] = f5;
-        L.rhs = -lp(LP_CI, lane);
+        L.rhs = act ? -lp(LP_CI, lane) : R(0);
+        L.dinv = R(1); L.tmp = R(0); L.zf = R(0);
       }
     GMR_END
     if (pinned) {
