@@ -8,6 +8,8 @@
 
 #define GMR_NH 32            // lanes of a warp = hinge DoFs (GMR_MAX_HINGE)
 #define GMR_MAX_LEVEL 64
+#define GMR_MAXD 14          // deepest chain of hinges root -> leaf the factorisation is unrolled for
+#define GMR_NS (6 + GMR_MAXD) // row slots of one hinge: 6 floating-base columns, then its ancestors by depth
 
 template <typename R>
 struct GmrConsts {
@@ -23,7 +25,13 @@ struct GmrConsts {
   int16_t tbody[GMR_MAX_TASK];        // task -> robot body
   int16_t thuman[GMR_MAX_TASK];       // task -> human body
   uint32_t anc_mask[GMR_NH];          // hinge i -> bitmask of hinges that are strict ancestors of i
+  uint32_t desc_mask[GMR_NH];         // hinge i -> bitmask of hinges that are strict descendants of i
   uint32_t task_mask[GMR_NH];         // hinge i -> bitmask of tasks whose body lies in i's subtree
+  int32_t maxd, tlmax, _pad2[2];      // deepest hinge chain; most tasks in any hinge's subtree
+  int16_t hl_off[GMR_MAXD + 2];       // hl_hinge[hl_off[d] .. hl_off[d+1]) are the hinges of depth d (1-based)
+  uint8_t hl_hinge[GMR_NH];           // hinges sorted by depth
+  uint8_t hdepth[GMR_NH];             // hinge i -> number of hinges on the chain root .. i (inclusive); 0 for unused lanes
+  uint8_t anc_of[GMR_NH * GMR_MAXD];  // [i][d-1] -> the hinge at depth d on i's chain (d <= hdepth[i]; own index at d = hdepth[i])
   R bpos[GMR_MAX_BODY * 3];
   R bquat[GMR_MAX_BODY * 4];
   R axis[GMR_NH * 3];
@@ -41,9 +49,10 @@ struct GmrConsts {
 struct GmrDims {
   int32_t nb, nh, nhum, nt, nlevel, nq, hroot, use1, use2, max_iter;
   uint32_t in1_mask, in2_mask, limited_mask, foot_mask;
+  int32_t maxd, tlmax;
   // per-warp shared-memory layout for the launching precision (element offsets, see gmr_solver.cuh)
   int32_t o_tg, o_in, o_xp, o_xq, o_u, warp_elems;
-  int16_t loff[GMR_NH + 2];   // packed factor-row offsets
+  int32_t o_y, rs;            // published factor row of a hinge: slots [0, o_y), then y, 1/d, 2 pad; stride rs
 };
 template <typename R> struct GmrScal { R damping, lm, gain, tol, dt; };
 
@@ -52,6 +61,8 @@ template <typename R> inline GmrDims gmr_dims_of(const GmrConsts<R>& c) {
   d.nb = c.nb; d.nh = c.nh; d.nhum = c.nhum; d.nt = c.nt; d.nlevel = c.nlevel; d.nq = c.nq; d.hroot = c.hroot;
   d.use1 = c.use1; d.use2 = c.use2; d.max_iter = c.max_iter;
   d.in1_mask = c.in1_mask; d.in2_mask = c.in2_mask; d.limited_mask = c.limited_mask; d.foot_mask = c.foot_mask;
+  d.maxd = c.maxd; d.tlmax = c.tlmax;
+  d.o_tg = d.o_in = d.o_xp = d.o_xq = d.o_u = d.warp_elems = d.o_y = d.rs = 0;
   return d;
 }
 template <typename R> inline GmrScal<R> gmr_scal_of(const GmrConsts<R>& c) {
@@ -120,6 +131,23 @@ inline int gmr_fill_consts(const GmrModelDesc* d, GmrConsts<R>* c, const char** 
     for (int b = m.parent[m.hbody[j]]; b >= 0; b = m.parent[b]) if (m.bhinge[b] >= 0) anc |= 1u << m.bhinge[b];
     m.anc_mask[j] = anc;
   }
+  // hinge depths, chains by depth, descendants, hinges grouped by depth (the elimination order of the
+  // branch-sparse factorisation: deepest hinges first)
+  m.maxd = 0;
+  for (int j = 0; j < m.nh; j++) {
+    int chain[GMR_MAX_BODY], n = 0;
+    for (int b = m.hbody[j]; b >= 0; b = m.parent[b]) if (m.bhinge[b] >= 0) chain[n++] = m.bhinge[b];
+    if (n > GMR_MAXD) return fail(GMR_ELIMIT, "hinge chain too deep (GMR_MAXD)");
+    m.hdepth[j] = (uint8_t)n;
+    if (n > m.maxd) m.maxd = n;
+    for (int d = 1; d <= n; d++) m.anc_of[j * GMR_MAXD + d - 1] = (uint8_t)chain[n - d];
+    for (int d = n + 1; d <= GMR_MAXD; d++) m.anc_of[j * GMR_MAXD + d - 1] = (uint8_t)j;
+    for (int i = 0; i < m.nh; i++) if ((m.anc_mask[j] >> i) & 1u) m.desc_mask[i] |= 1u << j;
+  }
+  { int n = 0;
+    m.hl_off[0] = 0;
+    for (int d = 1; d <= GMR_MAXD; d++) { m.hl_off[d] = (int16_t)n; for (int j = 0; j < m.nh; j++) if (m.hdepth[j] == d) m.hl_hinge[n++] = (uint8_t)j; }
+    m.hl_off[GMR_MAXD + 1] = (int16_t)n; }
   for (int i = 0; i < m.nq; i++) m.qpos0[i] = R(d->qpos0[i]);
   for (int i = 0; i < m.nhum; i++) {
     m.hscale[i] = R(d->human_scale[i]);
@@ -137,5 +165,7 @@ inline int gmr_fill_consts(const GmrModelDesc* d, GmrConsts<R>* c, const char** 
     if (d->task_in2[t]) m.in2_mask |= 1u << t;
     for (int bb = b; bb >= 0; bb = m.parent[bb]) if (m.bhinge[bb] >= 0) m.task_mask[m.bhinge[bb]] |= 1u << t;
   }
+  m.tlmax = 0;
+  for (int j = 0; j < m.nh; j++) { int n = 0; for (int t = 0; t < m.nt; t++) n += (m.task_mask[j] >> t) & 1u; if (n > m.tlmax) m.tlmax = n; }
   return GMR_OK;
 }

@@ -49,7 +49,9 @@
 #define GMR_BCAST2(src, f0, f1) } { const R bc0 = lanes_[src].f0, bc1 = lanes_[src].f1; for (int lane = 0; lane < 32; ++lane) { LaneRegs<R>& L = lanes_[lane]; (void)L;
 #define GMR_END_BCAST } }
 #define GMR_END_BCAST_NOSYNC } }
-#define GMR_OWN_OFF (dm.loff[lane])
+#define GMR_END_NOSYNC }
+#define GMR_DEPTH ((int)mc.hdepth[lane])
+#define GMR_CTZ(x) __builtin_ctz(x)
 #else
 #define GMR_FN __device__ __forceinline__
 #define GMR_HD __host__ __device__ inline
@@ -62,29 +64,27 @@
 #define GMR_BCAST2(src, f0, f1) const R bc0 = __shfl_sync(0xffffffffu, L.f0, src), bc1 = __shfl_sync(0xffffffffu, L.f1, src);
 #define GMR_END_BCAST } __syncwarp();
 #define GMR_END_BCAST_NOSYNC }
-#define GMR_OWN_OFF (own_off_)
+#define GMR_END_NOSYNC }
+#define GMR_DEPTH (dep_)
+#define GMR_CTZ(x) (__ffs(x) - 1)
 #endif
 
 // ---- shared-memory layout of one warp's state (units: elements of R) -----------------------
 GMR_HD constexpr int gmr_pad4(int n) { return (n + 3) & ~3; }
-// Packed storage of the factor rows.  Row i (lane i, block b = i / 4) holds
-//   [ a'(6) 0 0 | L_i0 .. L_i,i-1 | -1 at column i | zeros up to the end of its block of 4 columns ]
-// i.e. GMR_LC + 4 (b + 1) values: base columns at 0..5, hinge column m at GMR_LC + m.  The zero
-// tail and the -1 let every lane take a FIXED-LENGTH, statically indexed dot product with the
-// broadcast pivot row:  sum_m row_i[m] * lk[m] = sum_{m<k} L_im L_km - H_ik.
-#define GMR_LC 8
-GMR_HD constexpr int gmr_rlen(int b) { return GMR_LC + 4 * (b + 1); }
-GMR_HD constexpr int gmr_loff(int i) {
-  const int b = i >> 2, e = i & 3;
-  return 8 * b * b + 40 * b + e * (12 + 4 * b);
-}
+// Published factor row of hinge k (written when k is eliminated, read by its ancestors and by the
+// back substitution):  [ H'_k,base(6) | H'_k,anc(depth 1) .. H'_k,anc(depth d_k - 1) | junk up to o_y | y_k, 1/d_k, 0, 0 ]
+// Slots are indexed by the DEPTH of the ancestor, not by its hinge number: every hinge on the chain root .. k
+// sees the same ancestor at the same slot, which is what lets lane i update row_i[s] -= a * row_k[s] with
+// statically indexed registers.
+GMR_HD constexpr int gmr_row_oy(int maxd) { return gmr_pad4(6 + (maxd > 0 ? maxd : 1)); }
+GMR_HD constexpr int gmr_row_stride(int maxd) { return gmr_row_oy(maxd) + 4; }
 
 // fixed part
 enum {
   GS_RED = 0,               // [32] reductions / hand-over scratch
   GS_XS = 32,               // [40] solution of the last linear solve (base 6, hinges)
   GS_ROOT = 72,             // [28] whole-tree composite: M(21) g(6) mu
-  GS_LF = 100,              // [28] base 6x6 factor (21, reciprocal diagonal) + y_base(6)
+  GS_LF = 100,              // [28] base 6x6 Schur complement (21, packed upper) + its right-hand side (6)
   GS_PIV = 128,             // [4]
   GS_RQ = 132,              // [4] normalised root quaternion of the last FK
   GS_BND = 136,             // [32] bound value of pinned hinges
@@ -97,12 +97,13 @@ enum { LP_F = 0, LP_DIAG = 6, LP_CI = 7, LP_X = 8 };
 template <typename R> GMR_HD int gmr_in_elems(int nhum) { return gmr_pad4((int)((8 * nhum * sizeof(float) + sizeof(R) - 1) / sizeof(R))); }
 // variable part: sd[8nh] tg[8nhum] in[staged floats] U, where the union U holds
 //   [ mt: task inertias, max(28 nt, 64) | xp: pad4(3 nb) | xq: 4 nb ]   while FK / task evaluation are live, and
-//   [ packed factor rows, loff(nh) ]                                        from the factorisation to the next FK.
+//   [ published factor rows, nh * stride ]                                  from the factorisation to the next FK.
 // (body poses are dead once the composites are built; integrate() takes the root quaternion from GS_RQ.)
 GMR_HD constexpr int gmr_mt_elems(int nt) { return gmr_pad4(28 * nt > 64 ? 28 * nt : 64); }
-template <typename R> GMR_HD int gmr_warp_elems(int nb, int nh, int nhum, int nt) {
+template <typename R> GMR_HD int gmr_warp_elems(int nb, int nh, int nhum, int nt, int maxd) {
   int u = gmr_mt_elems(nt) + gmr_pad4(3 * nb) + 4 * nb;
-  if (gmr_loff(nh) > u) u = gmr_loff(nh);
+  const int lr = (nh > 0 ? nh : 1) * gmr_row_stride(maxd);
+  if (lr > u) u = lr;
   return GS_VAR + 8 * (nh > 0 ? nh : 1) + 8 * nhum + gmr_in_elems<R>(nhum) + gmr_pad4(u);
 }
 
@@ -114,8 +115,9 @@ template <typename R> inline void gmr_dims_layout(GmrDims& d) {
   d.o_u = o;
   d.o_xp = o + gmr_mt_elems(d.nt);
   d.o_xq = d.o_xp + gmr_pad4(3 * d.nb);
-  d.warp_elems = gmr_warp_elems<R>(d.nb, d.nh, d.nhum, d.nt);
-  for (int i = 0; i < GMR_NH + 2; i++) d.loff[i] = (int16_t)gmr_loff(i);
+  d.o_y = gmr_row_oy(d.maxd);
+  d.rs = gmr_row_stride(d.maxd);
+  d.warp_elems = gmr_warp_elems<R>(d.nb, d.nh, d.nhum, d.nt, d.maxd);
 }
 
 template <typename R> struct GmrEps;
@@ -127,9 +129,9 @@ template <> struct GmrEps<double> { static constexpr double lie = 2.220446049250
 // per-lane registers that persist across lane blocks (what the factorisation keeps live;
 // colder per-lane state sits in the lane-private shared-memory slots GS_LP)
 template <typename R> struct LaneRegs {
-  R a[6];          // base (floating joint) columns of this hinge's row of H, then of L
-  R row[GMR_NH];   // hinge columns j <= lane
-  R rhs, dinv, tmp, zf;
+  R row[GMR_NS];   // this hinge's row of H by slot: 6 floating-base columns, then its strict ancestors by depth
+  R dg;            // its diagonal
+  R rhs, dinv;
 };
 
 // ---- tiny math helpers ----------------------------------------------------------------------
@@ -195,6 +197,22 @@ GMR_FN void g_ld4(const double* p, double* v) {
 #else
   const double2 t = *reinterpret_cast<const double2*>(p), u = *reinterpret_cast<const double2*>(p + 2);
   v[0] = t.x; v[1] = t.y; v[2] = u.x; v[3] = u.y;
+#endif
+}
+
+// 4 consecutive elements to 16-byte aligned shared memory
+GMR_FN void g_st4(float* p, float a, float b, float c, float d) {
+#ifdef GMR_EMULATE
+  p[0] = a; p[1] = b; p[2] = c; p[3] = d;
+#else
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+#endif
+}
+GMR_FN void g_st4(double* p, double a, double b, double c, double d) {
+#ifdef GMR_EMULATE
+  p[0] = a; p[1] = b; p[2] = c; p[3] = d;
+#else
+  *reinterpret_cast<double2*>(p) = make_double2(a, b); *reinterpret_cast<double2*>(p + 2) = make_double2(c, d);
 #endif
 }
 
@@ -288,7 +306,7 @@ struct WarpSolver {
 #else
   LaneRegs<R> lanes_;
   int lane_;
-  int own_off_;                // offset of this lane's packed factor row
+  int dep_;                    // hinge depth of this lane (0: lane owns no hinge)
 #endif
   int stat_refactor;           // factorisations done (uniform)
   bool convoy;                 // CTA-wide rendezvous before every factorisation (see convoy_arrive)
@@ -304,7 +322,7 @@ struct WarpSolver {
                      : mc(m), dm(d), ks(k), stat_refactor(0), convoy(false), cta_active(nullptr), warm_lo(0), warm_hi(0) {
 #ifndef GMR_EMULATE
     lane_ = lane;
-    own_off_ = gmr_loff(lane);
+    dep_ = lane < d.nh ? (int)m.hdepth[lane] : 0;
     sm_off = smem_byte_off;
 #else
     sm = smem;
@@ -591,9 +609,13 @@ struct WarpSolver {
         R acc[28];
         GMR_UNROLL
         for (int i = 0; i < 28; i++) acc[i] = R(0);
-        const uint32_t tm = mc.task_mask[lane];
-        for (int t = 0; t < dm.nt; t++) {
-          if ((tm >> t) & 1u) {
+        // every lane walks its OWN list of subtree tasks (set bits of its mask); the trip count is the
+        // longest list of the robot, not the number of tasks
+        uint32_t tm = mc.task_mask[lane];
+        for (int it = 0; it < dm.tlmax; it++) {
+          if (tm) {
+            const int t = GMR_CTZ(tm);
+            tm &= tm - 1u;
             const R* m = s_mt() + 28 * t;
             GMR_UNROLL
             for (int c = 0; c < 7; c++) {
@@ -621,94 +643,169 @@ struct WarpSolver {
   GMR_FN R bound_lo(int j) const { return ((dm.limited_mask >> j) & 1u) ? -(ks.gain * (s_q()[7 + j] - mc.lo[j])) : -R(INFINITY); }
 
   // ------------------------------------------------------------------ rows of H -------------
-  // lane i: row[j] = f_i . s_j for hinge ancestors j, row[i] = diag, a[] = f_i (base columns are
-  // unit twists at the root origin, world-aligned), rhs = -c_i.  With pins: pinned lanes become
-  // identity rows with rhs = bound, free lanes move the pinned columns to the right-hand side.
-  GMR_FN void build_rows(uint32_t pinned) {
-    // every lane defines ALL of its row registers here (lanes >= nh get an identity row): a full
-    // redefinition is what tells the compiler that row[] is dead between two solves, so the
-    // phases in between (FK, task evaluation, composites) have the whole register file
+  // H_ij = f_i . s_j is non-zero only when j is an ancestor of i (or i of j): branch-induced sparsity.
+  // Lane i keeps its row by SLOT: row[0..5] = f_i (the base columns are unit twists at the root origin,
+  // world-aligned), row[5 + d] = f_i . s_(ancestor of i at depth d) for d < depth_i, dg = diagonal,
+  // rhs = -c_i.  Every lane defines ALL of its row registers here (lanes without a hinge get zeros): a
+  // full redefinition is what tells the compiler that row[] is dead between two solves.
+  GMR_FN void build_rows() {
     GMR_LANES
       {
         const bool act = lane < dm.nh;
-        const uint32_t am = act ? mc.anc_mask[lane] : 0u;
-        const R f0 = act ? lp(LP_F, lane) : R(0), f1 = act ? lp(LP_F + 1, lane) : R(0), f2 = act ? lp(LP_F + 2, lane) : R(0),
-                f3 = act ? lp(LP_F + 3, lane) : R(0), f4 = act ? lp(LP_F + 4, lane) : R(0), f5 = act ? lp(LP_F + 5, lane) : R(0);
-        const R dg = act ? lp(LP_DIAG, lane) : R(1);
+        const int dep = GMR_DEPTH;
+        R f[6];
         GMR_UNROLL
-        for (int j = 0; j < GMR_NH; j++) {
+        for (int g = 0; g < 6; g++) { f[g] = act ? lp(LP_F + g, lane) : R(0); L.row[g] = f[g]; }
+        GMR_UNROLL
+        for (int d = 1; d <= GMR_MAXD; d++) {
           R v = R(0);
-          if (j < dm.nh && ((am >> j) & 1u)) {
-            R s[8]; g_ld4(s_sd() + 8 * j, s); g_ld4(s_sd() + 8 * j + 4, s + 4);
-            v = f0 * s[0] + f1 * s[1] + f2 * s[2] + f3 * s[3] + f4 * s[4] + f5 * s[5];
+          if (d < dm.maxd) {                                   // no hinge has a strict ancestor at depth maxd
+            if (d < dep) {
+              const int j = mc.anc_of[lane * GMR_MAXD + d - 1];
+              R s[8]; g_ld4(s_sd() + 8 * j, s); g_ld4(s_sd() + 8 * j + 4, s + 4);
+              v = f[0] * s[0] + f[1] * s[1] + f[2] * s[2] + f[3] * s[3] + f[4] * s[4] + f[5] * s[5];
+            }
           }
-          L.row[j] = (j == lane) ? dg : v;
+          L.row[5 + d] = v;
         }
-        L.a[0] = f0; L.a[1] = f1; L.a[2] = f2; L.a[3] = f3; L.a[4] = f4; L.a[5] = f5;
+        L.dg = act ? lp(LP_DIAG, lane) : R(1);
         L.rhs = act ? -lp(LP_CI, lane) : R(0);
-        L.dinv = R(1); L.tmp = R(0); L.zf = R(0);
+        L.dinv = R(1);
       }
     GMR_END
-    if (pinned) {
-      // pinned lanes publish (their column of H) * bound; s_bnd holds the bound values
-      GMR_LANES
-        if (lane < dm.nh && ((pinned >> lane) & 1u)) {
-          const R bv = s_bnd()[lane];
-          R* o = s_L() + GMR_OWN_OFF;
+  }
+
+  // stores this lane's row slots, scaled by `sc`, into its published row
+  GMR_FN void publish_row(R* o, const LaneRegs<R>& L, R sc, int nchunk) const {
+    GMR_UNROLL
+    for (int c = 0; c < GMR_NS / 4; c++)
+      if (c < nchunk) g_st4(o + 4 * c, L.row[4 * c] * sc, L.row[4 * c + 1] * sc, L.row[4 * c + 2] * sc, L.row[4 * c + 3] * sc);
+  }
+
+  // Working set: a pinned hinge p keeps x_p = bound.  Its row becomes the identity with rhs = bound, its
+  // column moves to the right-hand side of every row coupled to it (ancestors, descendants, base).
+  GMR_FN void apply_pins(uint32_t pinned) {
+    const int nchunk_all = dm.o_y >> 2;
+    GMR_LANES
+      if (lane < dm.nh && ((pinned >> lane) & 1u))
+        publish_row(s_L() + dm.rs * lane, L, s_bnd()[lane], nchunk_all);      // (row of H) * bound
+    GMR_END
+    GMR_LANES
+      if (lane < dm.nh) {
+        const int dep = GMR_DEPTH;
+        if ((pinned >> lane) & 1u) {
           GMR_UNROLL
-          for (int g = 0; g < 6; g++) o[g] = L.a[g] * bv;
-          GMR_UNROLL
-          for (int j = 0; j < GMR_NH; j++) if (j < lane) o[GMR_LC + j] = L.row[j] * bv;
-        }
-      GMR_END
-      GMR_LANES
-        if (lane < dm.nh) {
-          if ((pinned >> lane) & 1u) {
+          for (int s = 0; s < GMR_NS; s++) L.row[s] = R(0);
+          L.dg = R(1);
+          L.rhs = s_bnd()[lane];
+        } else {
+          R r = L.rhs;
+          if (mc.anc_mask[lane] & pinned) {                     // pinned ancestors: my own slots
             GMR_UNROLL
-            for (int g = 0; g < 6; g++) L.a[g] = R(0);
-            GMR_UNROLL
-            for (int j = 0; j < GMR_NH; j++) L.row[j] = (j == lane) ? R(1) : R(0);
-            L.rhs = s_bnd()[lane];
-          } else {
-            R r = L.rhs;
-            GMR_UNROLL
-            for (int j = 0; j < GMR_NH; j++) {
-              if ((pinned >> j) & 1u) {
-                if (j < lane) { r -= L.row[j] * s_bnd()[j]; L.row[j] = R(0); }
-                else if (j > lane && j < dm.nh) r -= s_L()[dm.loff[j] + GMR_LC + lane];
+            for (int d = 1; d < GMR_MAXD; d++) {
+              if (d < dep) {
+                const int j = mc.anc_of[lane * GMR_MAXD + d - 1];
+                if ((pinned >> j) & 1u) { r -= L.row[5 + d] * s_bnd()[j]; L.row[5 + d] = R(0); }
               }
             }
-            L.rhs = r;
           }
+          uint32_t ds = mc.desc_mask[lane] & pinned;            // pinned descendants: their published rows
+          while (ds) { const int p = GMR_CTZ(ds); ds &= ds - 1u; r -= s_L()[dm.rs * p + 5 + dep]; }
+          L.rhs = r;
         }
-        // base right-hand side correction, gathered by lanes 0..5 into s_xs[0..5]
-        if (lane < 6) {
-          R r = R(0);
-          for (int j = 0; j < dm.nh; j++) if ((pinned >> j) & 1u) r += s_L()[dm.loff[j] + lane];
-          s_xs()[lane] = r;
-        }
-      GMR_END
-    }
+      }
+      if (lane < 6) {                                           // base right-hand side correction -> s_xs[0..5]
+        R r = R(0);
+        uint32_t ps = pinned;
+        while (ps) { const int p = GMR_CTZ(ps); ps &= ps - 1u; r += s_L()[dm.rs * p + lane]; }
+        s_xs()[lane] = r;
+      }
+    GMR_END
   }
 
   // ------------------------------------------------------------------ factor + solve --------
   // Solves H x = rhs for the rows built above; result in s_xs[0..nv) (base first).
-  GMR_FN void factor_solve(uint32_t pinned) {
-    // 6x6 base block (uniform data from s_root), factored by lane 0
+  //
+  // Branch-sparse L^T D L factorisation (the elimination order of Featherstone's sparse joint-space
+  // factorisation: leaves first, so no fill-in outside the ancestor pattern).  Hinges are eliminated by
+  // DEPTH, deepest first; all hinges of one depth publish their rows at once (one __syncwarp per depth),
+  // then every strict ancestor i of pivot k does  a = H_ki / d_k;  row_i[s] -= a * row_k[s]  over the
+  // pivot's slots (the same slot is the same ancestor for both),  d_i -= a * H_ki,  rhs_i -= a * y_k
+  // (the forward substitution rides along).  The 6 floating-base DoFs are the ancestors of everything:
+  // their 6x6 Schur complement is accumulated afterwards by 27 lanes (21 entries + 6 right-hand sides) from
+  // the published rows and solved densely; the back substitution walks the depths root -> leaves.
+  // For G1: 10 depths instead of 29 sequential pivots, rows of <= 16 slots instead of 35.
+  GMR_FN void factor_solve(bool pinned_any) {
+    for (int lv = dm.maxd; lv >= 1; lv--) {
+      const int beg = mc.hl_off[lv], end = mc.hl_off[lv + 1];
+      const int nchunk = (5 + lv + 3) >> 2;                     // slots [0, 5 + lv) = base + strict ancestors
+      GMR_LANES
+        if (GMR_DEPTH == lv) {
+          const R di = R(1) / L.dg;
+          L.dinv = di;
+          R* o = s_L() + dm.rs * lane;
+          publish_row(o, L, R(1), nchunk);
+          g_st4(o + dm.o_y, L.rhs, di, R(0), R(0));
+        }
+      GMR_END
+      for (int e = beg; e < end; e++) {
+        const int k = mc.hl_hinge[e];
+        const uint32_t am = mc.anc_mask[k];
+        GMR_LANES
+          if ((am >> lane) & 1u) {
+            const R* pk = s_L() + dm.rs * k;
+            const R hki = pk[5 + GMR_DEPTH];
+            const R yk = pk[dm.o_y], dk = pk[dm.o_y + 1];
+            const R a = hki * dk;
+            GMR_UNROLL
+            for (int c = 0; c < GMR_NS / 4; c++) {
+              if (c < nchunk) {
+                R v[4]; g_ld4(pk + 4 * c, v);
+                L.row[4 * c] -= a * v[0]; L.row[4 * c + 1] -= a * v[1]; L.row[4 * c + 2] -= a * v[2]; L.row[4 * c + 3] -= a * v[3];
+              }
+            }
+            L.dg -= a * hki;
+            L.rhs -= a * yk;
+          }
+        GMR_END_NOSYNC
+      }
+    }
+    GMR_SYNC();
+    // base block: S = A_bb - sum_k (1/d_k) h_k h_k^T,  b = b_b - sum_k (1/d_k) h_k y_k,  h_k = published base slots
+    GMR_LANES
+      if (lane < 27) {
+        int r, cc;
+        if (lane < 21) {
+          r = (lane >= 6) + (lane >= 11) + (lane >= 15) + (lane >= 18) + (lane >= 20);
+          cc = r + lane - (r * (13 - r)) / 2;
+        } else { r = lane - 21; cc = dm.o_y; }
+        R acc0 = R(0), acc1 = R(0);
+        int k = 0;
+        for (; k + 1 < dm.nh; k += 2) {
+          const R* p0 = s_L() + dm.rs * k;
+          const R* p1 = p0 + dm.rs;
+          acc0 += p0[r] * p0[dm.o_y + 1] * p0[cc];
+          acc1 += p1[r] * p1[dm.o_y + 1] * p1[cc];
+        }
+        if (k < dm.nh) { const R* p0 = s_L() + dm.rs * k; acc0 += p0[r] * p0[dm.o_y + 1] * p0[cc]; }
+        const R* rt = s_root();
+        R v;
+        if (lane < 21) v = rt[lane] + ((cc == r) ? ks.damping + rt[27] : R(0));
+        else v = -rt[lane] - (pinned_any ? s_xs()[r] : R(0));
+        s_lf()[lane] = v - (acc0 + acc1);
+      }
+    GMR_END
+    // dense 6x6 solve by lane 0: S = Lf Lf^T, x_b = Lf^-T Lf^-1 b
     GMR_LANES
       if (lane == 0) {
-        const R* c = s_root();
-        const R dd = ks.damping + c[27];
+        const R* c = s_lf();
         R A[21];
         GMR_UNROLL
         for (int i = 0; i < 21; i++) A[i] = c[i];
+        R y[6];
         GMR_UNROLL
-        for (int i = 0; i < 6; i++) A[gmr_sym6(i, i)] += dd;
-        R b[6];
-        GMR_UNROLL
-        for (int i = 0; i < 6; i++) b[i] = -c[21 + i] - (pinned ? s_xs()[i] : R(0));
-        // Cholesky A = Lf Lf^T, Lf stored row-wise lower: lf[i*(i+1)/2 + j]
-        R lf[21];
+        for (int i = 0; i < 6; i++) y[i] = c[21 + i];
+        R lf[21];                                              // row-wise lower, reciprocal diagonal
         GMR_UNROLL
         for (int i = 0; i < 6; i++) {
           GMR_UNROLL
@@ -716,138 +813,19 @@ struct WarpSolver {
             R s = A[gmr_sym6(j, i)];
             GMR_UNROLL
             for (int k = 0; k < j; k++) s -= lf[i * (i + 1) / 2 + k] * lf[j * (j + 1) / 2 + k];
-            if (i == j) lf[i * (i + 1) / 2 + i] = g_rsqrt(s);            // reciprocal diagonal 1 / L_ii
+            if (i == j) lf[i * (i + 1) / 2 + i] = g_rsqrt(s);
             else lf[i * (i + 1) / 2 + j] = s * lf[j * (j + 1) / 2 + j];
           }
-        }
-        // yf = Lf^-1 b
-        R y[6];
-        GMR_UNROLL
-        for (int i = 0; i < 6; i++) {
-          R s = b[i];
+          R s = y[i];
           GMR_UNROLL
           for (int k = 0; k < i; k++) s -= lf[i * (i + 1) / 2 + k] * y[k];
           y[i] = s * lf[i * (i + 1) / 2 + i];
         }
-        R* o = s_lf();
-        GMR_UNROLL
-        for (int i = 0; i < 21; i++) o[i] = lf[i];
-        GMR_UNROLL
-        for (int i = 0; i < 6; i++) o[21 + i] = y[i];
-      }
-    GMR_END
-    // every hinge row: a' = a Lf^-T (forward substitution on its own 6 values), rhs -= a'.yf
-    GMR_LANES
-      if (lane < dm.nh) {
-        R lf[28];
-        GMR_UNROLL
-        for (int c = 0; c < 7; c++) g_ld4(s_lf() + 4 * c, lf + 4 * c);
-        R r = L.rhs;
-        GMR_UNROLL
-        for (int i = 0; i < 6; i++) {
-          R s = L.a[i];
-          GMR_UNROLL
-          for (int k = 0; k < i; k++) s -= lf[i * (i + 1) / 2 + k] * L.a[k];
-          s *= lf[i * (i + 1) / 2 + i];
-          L.a[i] = s;
-          r -= s * lf[21 + i];
-        }
-        L.rhs = r;
-        // initialise this lane's packed row: a', two pad zeros, zeros over its hinge columns, -1 on the diagonal
-        R* o = s_L() + GMR_OWN_OFF;
-        GMR_UNROLL
-        for (int g = 0; g < 6; g++) o[g] = L.a[g];
-        o[6] = R(0); o[7] = R(0);
-        const int nc = 4 * ((lane >> 2) + 1);
-        for (int j = 0; j < nc; j++) o[GMR_LC + j] = (j == lane) ? R(-1) : R(0);
-      }
-    GMR_END
-    // hinge block, column by column.  Pivots are taken in blocks of 4: the outer loop over blocks is
-    // ROLLED (one copy of the block in the instruction stream — the kernel is instruction-supply
-    // bound), inside a block the registers are indexed statically and the only
-    // block-dependent register access — storing the new column into row[4b+e] — goes through an
-    // 8-way switch.  Lane k hands 1/L_kk and y_k to the other lanes with two shuffles; one
-    // __syncwarp per pivot orders the shared-memory row writes.
-    const int nblk = (dm.nh + 3) >> 2;
-    for (int b = 0; b < nblk; b++) {
-      const int nchunk = 3 + b;                         // pivot row length = 4 * (3 + b)
-      GMR_UNROLL
-      for (int e = 0; e < 4; e++) {
-        const int k = 4 * b + e;
-        if (k < dm.nh) {
-          GMR_LANES
-            if (lane >= k && lane < dm.nh) {
-              const R* lk = s_L() + dm.loff[k];
-              R s0 = R(0), s1 = R(0);
-              GMR_UNROLL
-              for (int c = 0; c < 2 + GMR_NH / 4; c++) {
-                if (c < nchunk) {
-                  R v[4]; g_ld4(lk + 4 * c, v);
-                  GMR_UNROLL
-                  for (int u = 0; u < 4; u++) {
-                    const int p = 4 * c + u;
-                    if (p < 6) { if (u & 1) s1 += L.a[p < 6 ? p : 0] * v[u]; else s0 += L.a[p < 6 ? p : 0] * v[u]; }
-                    else if (p >= GMR_LC) {
-                      const int m = (p >= GMR_LC && p < GMR_LC + GMR_NH) ? p - GMR_LC : 0;
-                      if (u & 1) s1 += L.row[m] * v[u]; else s0 += L.row[m] * v[u];
-                    }
-                  }
-                }
-              }
-              const R s = -(s0 + s1);                    // = H_ik - sum_{m<k} L_im L_km (base columns included)
-              if (lane == k) {
-                const R di = g_rsqrt(s);
-                L.dinv = di; L.rhs *= di; L.tmp = di;
-              } else {
-                L.tmp = s;
-              }
-            }
-          GMR_BCAST2(k, tmp, rhs)
-            if (lane > k && lane < dm.nh) {
-              const R l = L.tmp * bc0;
-              switch (b) {
-                case 0: L.row[0 + e] = l; break;
-                case 1: L.row[4 + e] = l; break;
-                case 2: L.row[8 + e] = l; break;
-                case 3: L.row[12 + e] = l; break;
-                case 4: L.row[16 + e] = l; break;
-                case 5: L.row[20 + e] = l; break;
-                case 6: L.row[24 + e] = l; break;
-                default: L.row[28 + e] = l; break;
-              }
-              s_L()[GMR_OWN_OFF + GMR_LC + k] = l;
-              L.rhs -= l * bc1;
-            }
-          GMR_END_BCAST
-        }
-      }
-    }
-    // back substitution: hinges from the last to the first, lanes 0..5 also accumulate A'^T x
-    GMR_LANES
-      L.zf = (lane < 6) ? s_lf()[21 + lane] : R(0);      // zf accumulators (lanes 0..5)
-    GMR_END
-    for (int k = dm.nh - 1; k >= 0; k--) {
-      GMR_LANES
-        if (lane == k) { L.tmp = L.rhs * L.dinv; s_xs()[6 + k] = L.tmp; }
-      GMR_BCAST1(k, tmp)
-        const R* lk = s_L() + dm.loff[k];
-        if (lane < k) L.rhs -= lk[GMR_LC + lane] * bc0;
-        if (lane < 6) L.zf -= lk[lane] * bc0;
-      GMR_END_BCAST_NOSYNC
-    }
-    GMR_LANES
-      if (lane < 6) s_xs()[lane] = L.zf;   // zf = yf - A'^T x_h
-    GMR_END
-    GMR_LANES
-      if (lane == 0) {                                     // x_f = Lf^-T zf
-        const R* lf = s_lf();
-        R z[6], x[6];
-        GMR_UNROLL
-        for (int i = 0; i < 6; i++) z[i] = s_xs()[i];
+        R x[6];
         GMR_UNROLL
         for (int ii = 0; ii < 6; ii++) {
           const int i = 5 - ii;
-          R s = z[i];
+          R s = y[i];
           GMR_UNROLL
           for (int k = i + 1; k < 6; k++) s -= lf[k * (k + 1) / 2 + i] * x[k];
           x[i] = s * lf[i * (i + 1) / 2 + i];
@@ -856,6 +834,31 @@ struct WarpSolver {
         for (int i = 0; i < 6; i++) s_xs()[i] = x[i];
       }
     GMR_END
+    // back substitution, root -> leaves:  x_k = (y_k - sum_s row_k[s] x_(anc at slot s)) / d_k
+    GMR_LANES
+      if (lane < dm.nh) {
+        R acc = L.rhs;
+        GMR_UNROLL
+        for (int c = 0; c < 6; c++) acc -= L.row[c] * s_xs()[c];
+        L.rhs = acc;
+      }
+    GMR_END_NOSYNC
+    GMR_UNROLL
+    for (int lv = 1; lv <= GMR_MAXD; lv++) {
+      if (lv <= dm.maxd) {
+        GMR_LANES
+          if (GMR_DEPTH == lv) s_xs()[6 + lane] = L.rhs * L.dinv;
+        GMR_END
+        if (lv < dm.maxd) {
+          GMR_LANES
+            if (GMR_DEPTH > lv) {
+              const int j = mc.anc_of[lane * GMR_MAXD + lv - 1];
+              L.rhs -= L.row[5 + lv] * s_xs()[6 + j];
+            }
+          GMR_END_NOSYNC
+        }
+      }
+    }
   }
 
   // ------------------------------------------------------------------ box QP (A10, A11) -----
@@ -889,14 +892,16 @@ struct WarpSolver {
         GMR_END
       }
       if (!check) convoy_arrive();
-      build_rows(check ? 0u : pinned);
+      build_rows();
       if (!check) {
-        factor_solve(pinned);
+        if (pinned) apply_pins(pinned);
+        factor_solve(pinned != 0);
         stat_refactor++;
         // ratio test towards the candidate
+        bool blocked = false;
         GMR_LANES
+          R al = INF;
           if (lane < dm.nh) {
-            R al = INF;
             const R x = lp(LP_X, lane);
             if (!((pinned >> lane) & 1u)) {
               const R p = s_xs()[6 + lane] - x;
@@ -908,11 +913,16 @@ struct WarpSolver {
             }
             s_red()[lane] = al;
           }
+#ifdef GMR_EMULATE
+          if (al < R(1)) blocked = true;
+#else
+          blocked = __any_sync(0xffffffffu, al < R(1));
+#endif
         GMR_END
-        R alpha = R(1); int blk = -1;
-        for (int j = 0; j < dm.nh; j++) { const R a = s_red()[j]; if (a < alpha) { alpha = a; blk = j; } }
-        GMR_SYNC();
-        if (blk >= 0) {
+        if (blocked) {
+          R alpha = R(1); int blk = -1;
+          for (int j = 0; j < dm.nh; j++) { const R a = s_red()[j]; if (a < alpha) { alpha = a; blk = j; } }
+          GMR_SYNC();
           if (alpha < R(0)) alpha = R(0);
           GMR_LANES
             if (lane < dm.nh) {
@@ -938,25 +948,24 @@ struct WarpSolver {
         check = true;
         continue;
       }
-      // CHECK pass: g = H x + c on the original rows (just rebuilt); x is in s_xs
+      // CHECK pass: g = H x + c on the original rows (just rebuilt); x is in s_xs.  Every lane publishes
+      // (its row) * x_lane, a pinned lane adds its own slots times the ancestors' x and collects its
+      // column from the published rows of its descendants.
       GMR_LANES
-        if (lane < dm.nh) {
-          R* o = s_L() + GMR_OWN_OFF;
-          const R x = lp(LP_X, lane);
-          GMR_UNROLL
-          for (int j = 0; j < GMR_NH; j++) if (j < lane) o[GMR_LC + j] = L.row[j] * x;
-        }
+        if (lane < dm.nh) publish_row(s_L() + dm.rs * lane, L, lp(LP_X, lane), dm.o_y >> 2);
       GMR_END
       GMR_LANES
         if (lane < dm.nh) {
           R lam = INF;
           if ((pinned >> lane) & 1u) {
-            R g = lp(LP_CI, lane) + lp(LP_DIAG, lane) * lp(LP_X, lane);
+            const int dep = GMR_DEPTH;
+            R g = lp(LP_CI, lane) + L.dg * lp(LP_X, lane);
             GMR_UNROLL
-            for (int f = 0; f < 6; f++) g += L.a[f] * s_xs()[f];
+            for (int f = 0; f < 6; f++) g += L.row[f] * s_xs()[f];
             GMR_UNROLL
-            for (int j = 0; j < GMR_NH; j++) if (j < lane) g += L.row[j] * s_xs()[6 + j];
-            for (int i = lane + 1; i < dm.nh; i++) g += s_L()[dm.loff[i] + GMR_LC + lane];
+            for (int d = 1; d < GMR_MAXD; d++) if (d < dep) g += L.row[5 + d] * s_xs()[6 + mc.anc_of[lane * GMR_MAXD + d - 1]];
+            uint32_t ds = mc.desc_mask[lane];
+            while (ds) { const int k = GMR_CTZ(ds); ds &= ds - 1u; g += s_L()[dm.rs * k + 5 + dep]; }
             lam = ((pin_lo >> lane) & 1u) ? g : -g;
           }
           s_red()[lane] = lam;

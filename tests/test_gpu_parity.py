@@ -97,10 +97,12 @@ def test_known_answer_vectors(lib, torch_cuda):
         src, robot = key.split("_", 1)
         m, tt, _ = problem(src, robot)
         ratio = (g[key + ".heights"].astype(np.float64) / float(tt.height_assumption)).astype(np.float32)
-        for bits, tol in ((64, 1e-3), (32, 1e-3)):
+        # float64: identical iteration counts.  float32: the loop exit `curr - next > 1e-3` is a knife edge, a
+        # couple of the 25-120 frames of a fixture may take one IK step more or less
+        for bits, tol, min_agree in ((64, 1e-3, 1.0), (32, 1e-3, 0.95)):
             q, it, err = capi_run(lib, torch_cuda, m, tt, g[key + ".pos"], g[key + ".quat"], ratio, bits=bits)
             agree, dq_all, dq_clean = compare(q, it, g[key + ".qpos"], g[key + ".iters"])
-            assert agree >= 0.97 and dq_clean < tol, (key, bits, agree, dq_clean)
+            assert agree >= min_agree and dq_clean < tol, (key, bits, agree, dq_clean)
 
 
 @pytest.mark.parametrize("src,robot", [("smplx", "stanford_toddy"), ("bvh", "booster_t1"), ("smplx", "unitree_g1")])
