@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(MAXWARPS * 32, 1)
 gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ GmrScal<R> ks,
                     const GmrConsts<R>* __restrict__ gconsts, const float* __restrict__ pos, const float* __restrict__ quat,
                     const float* __restrict__ ratio, int C, int T, const IO* __restrict__ qinit, IO* __restrict__ qout,
-                    int32_t* __restrict__ iters, IO* __restrict__ err, IO* __restrict__ tg, uint32_t flags) {
+                    int32_t* __restrict__ iters, IO* __restrict__ err, IO* __restrict__ tg, uint32_t flags,
+                    int* __restrict__ queue) {
   extern __shared__ __align__(128) unsigned char gmr_dyn_smem[];
   unsigned char* const smem = gmr_dyn_smem;
   constexpr int CB = consts_bytes<R>();
@@ -82,19 +83,26 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
     __syncthreads();
   }
   const int nq = dm.nq, nhum = dm.nhum;
+  // Clips come from a global queue (one atomic per clip): clips differ several-fold in the number of
+  // IK steps they need, so a warp that finishes early takes the next clip instead of idling behind a
+  // static assignment.  The first gridDim * wpc clips are handed out without touching the queue.
   const int nw = gridDim.x * wpc;
-  for (int c = warp * gridDim.x + blockIdx.x; c < C; c += nw) {
+  for (int c = warp * gridDim.x + blockIdx.x; c < C;) {
     const size_t f0 = (size_t)c * T;
     ws.template run_clip<IO>(pos + f0 * nhum * 3, quat + f0 * nhum * 4, ratio ? R(ratio[c]) : R(1), T,
                              qinit ? qinit + (size_t)c * nq : nullptr, qout + f0 * nq,
                              iters ? iters + 2 * f0 : nullptr, err ? err + 2 * f0 : nullptr,
                              tg ? tg + f0 * nhum * 7 : nullptr, flags);
+    int nxt = 0;
+    if (lane == 0) nxt = nw + atomicAdd(queue, 1);
+    c = __shfl_sync(0xffffffffu, nxt, 0);
   }
   ws.convoy_retire();
 }
 
+constexpr int QUEUE_RING = 256;
 constexpr int MAXW_F32 = 28;   // 28 warps * 32 lanes * 72 registers = one SM's register file
-constexpr int MAXW_F64 = 14;   // 14 warps * 32 lanes * 144 registers
+constexpr int MAXW_F64 = 16;   // 16 warps * 32 lanes * 128 registers
 
 }  // namespace
 
@@ -109,6 +117,8 @@ struct GmrModel {
   GmrScal<float> ks32{};
   GmrScal<double> ks64{};
   int wel32 = 0, wel64 = 0;      // per-warp shared-memory elements
+  int* d_queue = nullptr;        // ring of clip-queue counters, one per launch in flight
+  std::atomic<uint32_t> queue_next{0};
   // lazily created resources of the host-buffer entry
   std::mutex host_mu;
   cudaStream_t hs[2] = {nullptr, nullptr};
@@ -174,7 +184,9 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
   static const int cv_env = getenv("GMR_CONVOY") ? atoi(getenv("GMR_CONVOY")) : -1;
   const bool convoy = cv_env >= 0 ? cv_env != 0 : wpc >= 8;
   flags = (flags & 0xffffu) | (convoy ? GMR_FLAG_INTERNAL_CONVOY : 0u);
-  kern<<<grid, wpc * 32, smem, st>>>(sizeof(R) == 4 ? m->dims32 : m->dims64, scal_of<R>(m), dc, pos, quat, ratio, C, T, qinit, qout, iters, err, tg, flags);
+  int* queue = m->d_queue + (m->queue_next.fetch_add(1) % QUEUE_RING);
+  CK(cudaMemsetAsync(queue, 0, sizeof(int), st));
+  kern<<<grid, wpc * 32, smem, st>>>(sizeof(R) == 4 ? m->dims32 : m->dims64, scal_of<R>(m), dc, pos, quat, ratio, C, T, qinit, qout, iters, err, tg, flags, queue);
   g_launches.fetch_add(1);
   CK(cudaGetLastError());
   return GMR_OK;
@@ -208,6 +220,7 @@ int gmr_model_create(const GmrModelDesc* desc, int device, GmrModel** out) {
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   if (e == cudaSuccess) e = cudaMalloc(&m->d_f32, consts_bytes<float>());
   if (e == cudaSuccess) e = cudaMalloc(&m->d_f64, consts_bytes<double>());
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_queue, QUEUE_RING * sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(m->d_f32, 0, consts_bytes<float>());
   if (e == cudaSuccess) e = cudaMemset(m->d_f64, 0, consts_bytes<double>());
   if (e == cudaSuccess) e = cudaMemcpy(m->d_f32, &m->h_f32, sizeof(GmrConsts<float>), cudaMemcpyHostToDevice);
@@ -217,11 +230,12 @@ int gmr_model_create(const GmrModelDesc* desc, int device, GmrModel** out) {
     int code = cuda_err(e, "gmr_model_create");
     if (m->d_f32) cudaFree(m->d_f32);
     if (m->d_f64) cudaFree(m->d_f64);
+    if (m->d_queue) cudaFree(m->d_queue);
     delete m;
     return code;
   }
   if (smem_bytes<float>(m, 1) > (size_t)m->max_smem) {
-    cudaFree(m->d_f32); cudaFree(m->d_f64); delete m;
+    cudaFree(m->d_f32); cudaFree(m->d_f64); cudaFree(m->d_queue); delete m;
     return set_err(GMR_ELIMIT, "model does not fit in shared memory");
   }
   *out = m;
@@ -237,6 +251,7 @@ int gmr_model_destroy(GmrModel* m) {
   }
   cudaFree(m->d_f32);
   cudaFree(m->d_f64);
+  cudaFree(m->d_queue);
   delete m;
   return GMR_OK;
 }
