@@ -28,12 +28,16 @@ struct GmrConsts {
   uint32_t desc_mask[GMR_NH];         // hinge i -> bitmask of hinges that are strict descendants of i
   uint32_t task_mask[GMR_NH];         // hinge i -> bitmask of tasks whose body lies in i's subtree
   int32_t maxd, tlmax, _pad2[2];      // deepest hinge chain; most tasks in any hinge's subtree
-  int16_t hl_off[GMR_MAXD + 2];       // hl_hinge[hl_off[d] .. hl_off[d+1]) are the hinges of depth d (1-based)
-  uint8_t hl_hinge[GMR_NH];           // hinges sorted by depth
+  uint32_t lvl_mask[GMR_MAXD + 2];    // [d] -> bitmask of the hinges of depth d (1-based)
   uint8_t hdepth[GMR_NH];             // hinge i -> number of hinges on the chain root .. i (inclusive); 0 for unused lanes
   uint8_t anc_of[GMR_NH * GMR_MAXD];  // [i][d-1] -> the hinge at depth d on i's chain (d <= hdepth[i]; own index at d = hdepth[i])
-  R bpos[GMR_MAX_BODY * 3];
-  R bquat[GMR_MAX_BODY * 4];
+  // forward-kinematics records, one per body in level order (entry e of lvl_body): what one lane needs to
+  // place its body, in three 128-bit loads.  The body's rotation in the parent frame is
+  // bquat * quat(axis, q) = cos(q/2) * A + sin(q/2) * B  with A = bquat, B = bquat * (0, axis).
+  uint32_t fk_idx[GMR_MAX_BODY];      // body | parent << 8 | (hinge, or nh for a fixed body) << 16
+  alignas(16) R fk_pos[GMR_MAX_BODY * 4];   // offset in the parent frame, pad (16-byte aligned: read with 128-bit loads)
+  alignas(16) R fk_A[GMR_MAX_BODY * 4];
+  alignas(16) R fk_B[GMR_MAX_BODY * 4];     // zero for a fixed body
   R axis[GMR_NH * 3];
   R lo[GMR_NH], hi[GMR_NH];
   R qpos0[8 + GMR_NH];
@@ -106,8 +110,6 @@ inline int gmr_fill_consts(const GmrModelDesc* d, GmrConsts<R>* c, const char** 
     int j = d->body_hinge[b];
     if (j < -1 || j >= m.nh || (b == 0 && j != -1)) return fail(GMR_EINVAL, "body_hinge out of range");
     m.bhinge[b] = (int16_t)j;
-    for (int k = 0; k < 3; k++) m.bpos[3 * b + k] = R(d->body_pos[3 * b + k]);
-    for (int k = 0; k < 4; k++) m.bquat[4 * b + k] = R(d->body_quat[4 * b + k]);
   }
   if (maxdepth + 1 > GMR_MAX_LEVEL) return fail(GMR_ELIMIT, "kinematic tree too deep");
   m.nlevel = maxdepth + 1;
@@ -144,10 +146,21 @@ inline int gmr_fill_consts(const GmrModelDesc* d, GmrConsts<R>* c, const char** 
     for (int d = n + 1; d <= GMR_MAXD; d++) m.anc_of[j * GMR_MAXD + d - 1] = (uint8_t)j;
     for (int i = 0; i < m.nh; i++) if ((m.anc_mask[j] >> i) & 1u) m.desc_mask[i] |= 1u << j;
   }
-  { int n = 0;
-    m.hl_off[0] = 0;
-    for (int d = 1; d <= GMR_MAXD; d++) { m.hl_off[d] = (int16_t)n; for (int j = 0; j < m.nh; j++) if (m.hdepth[j] == d) m.hl_hinge[n++] = (uint8_t)j; }
-    m.hl_off[GMR_MAXD + 1] = (int16_t)n; }
+  for (int j = 0; j < m.nh; j++) m.lvl_mask[m.hdepth[j]] |= 1u << j;
+  for (int e = 0; e < m.nb; e++) {
+    const int b = m.lvl_body[e], j = m.bhinge[b];
+    m.fk_idx[e] = (uint32_t)b | ((uint32_t)(m.parent[b] < 0 ? 0 : m.parent[b]) << 8) | ((uint32_t)(j >= 0 ? j : m.nh) << 16);
+    const double* bq = d->body_quat + 4 * b;
+    for (int k = 0; k < 3; k++) m.fk_pos[4 * e + k] = R(d->body_pos[3 * b + k]);
+    for (int k = 0; k < 4; k++) m.fk_A[4 * e + k] = R(bq[k]);
+    if (j >= 0) {
+      const double* ax = d->hinge_axis + 3 * j;                 // bquat * (0, axis)
+      m.fk_B[4 * e + 0] = R(-bq[1] * ax[0] - bq[2] * ax[1] - bq[3] * ax[2]);
+      m.fk_B[4 * e + 1] = R(bq[0] * ax[0] + bq[2] * ax[2] - bq[3] * ax[1]);
+      m.fk_B[4 * e + 2] = R(bq[0] * ax[1] - bq[1] * ax[2] + bq[3] * ax[0]);
+      m.fk_B[4 * e + 3] = R(bq[0] * ax[2] + bq[1] * ax[1] - bq[2] * ax[0]);
+    }
+  }
   for (int i = 0; i < m.nq; i++) m.qpos0[i] = R(d->qpos0[i]);
   for (int i = 0; i < m.nhum; i++) {
     m.hscale[i] = R(d->human_scale[i]);

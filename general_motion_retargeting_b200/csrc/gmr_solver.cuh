@@ -51,6 +51,9 @@
 #define GMR_END_BCAST_NOSYNC } }
 #define GMR_END_NOSYNC }
 #define GMR_DEPTH ((int)mc.hdepth[lane])
+#define GMR_DESC (mc.desc_mask[lane])
+#define GMR_SR (gmr_schur_r(lane))
+#define GMR_SC (gmr_schur_c(lane, dm.o_y))
 #define GMR_CTZ(x) __builtin_ctz(x)
 #else
 #define GMR_FN __device__ __forceinline__
@@ -66,6 +69,9 @@
 #define GMR_END_BCAST_NOSYNC }
 #define GMR_END_NOSYNC }
 #define GMR_DEPTH (dep_)
+#define GMR_DESC (desc_)
+#define GMR_SR (sr_)
+#define GMR_SC (sc_)
 #define GMR_CTZ(x) (__ffs(x) - 1)
 #endif
 
@@ -96,12 +102,12 @@ enum { LP_F = 0, LP_DIAG = 6, LP_CI = 7, LP_X = 8 };
 
 template <typename R> GMR_HD int gmr_in_elems(int nhum) { return gmr_pad4((int)((8 * nhum * sizeof(float) + sizeof(R) - 1) / sizeof(R))); }
 // variable part: sd[8nh] tg[8nhum] in[staged floats] U, where the union U holds
-//   [ mt: task inertias, max(28 nt, 64) | xp: pad4(3 nb) | xq: 4 nb ]   while FK / task evaluation are live, and
+//   [ mt: task inertias, max(28 nt, 72) | xp: 4 nb | xq: 4 nb ]          while FK / task evaluation are live, and
 //   [ published factor rows, nh * stride ]                                  from the factorisation to the next FK.
 // (body poses are dead once the composites are built; integrate() takes the root quaternion from GS_RQ.)
-GMR_HD constexpr int gmr_mt_elems(int nt) { return gmr_pad4(28 * nt > 64 ? 28 * nt : 64); }
+GMR_HD constexpr int gmr_mt_elems(int nt) { return gmr_pad4(28 * nt > 72 ? 28 * nt : 72); }   // >= 2 (GMR_NH + 1) + pad for the FK sin/cos table
 template <typename R> GMR_HD int gmr_warp_elems(int nb, int nh, int nhum, int nt, int maxd) {
-  int u = gmr_mt_elems(nt) + gmr_pad4(3 * nb) + 4 * nb;
+  int u = gmr_mt_elems(nt) + 4 * nb + 4 * nb;
   const int lr = (nh > 0 ? nh : 1) * gmr_row_stride(maxd);
   if (lr > u) u = lr;
   return GS_VAR + 8 * (nh > 0 ? nh : 1) + 8 * nhum + gmr_in_elems<R>(nhum) + gmr_pad4(u);
@@ -114,7 +120,7 @@ template <typename R> inline void gmr_dims_layout(GmrDims& d) {
   d.o_in = o; o += gmr_in_elems<R>(d.nhum);
   d.o_u = o;
   d.o_xp = o + gmr_mt_elems(d.nt);
-  d.o_xq = d.o_xp + gmr_pad4(3 * d.nb);
+  d.o_xq = d.o_xp + 4 * d.nb;
   d.o_y = gmr_row_oy(d.maxd);
   d.rs = gmr_row_stride(d.maxd);
   d.warp_elems = gmr_warp_elems<R>(d.nb, d.nh, d.nhum, d.nt, d.maxd);
@@ -132,6 +138,7 @@ template <typename R> struct LaneRegs {
   R row[GMR_NS];   // this hinge's row of H by slot: 6 floating-base columns, then its strict ancestors by depth
   R dg;            // its diagonal
   R rhs, dinv;
+  R sacc;          // lanes 0..26: one entry of the base block's Schur complement (accumulated during the elimination)
 };
 
 // ---- tiny math helpers ----------------------------------------------------------------------
@@ -176,6 +183,20 @@ template <typename R> GMR_FN void g_sincos(R x, R* s, R* c) {
   *s = (q & 2) ? -ss : ss;
   *c = ((q + 1) & 2) ? -cc : cc;
 }
+// reciprocal of a pivot (x >= damping > 0, far from the range limits): hardware seed + Newton steps, no slow path
+template <typename R> GMR_FN R g_rcp_pos(R x) { return R(1) / x; }
+#ifndef GMR_EMULATE
+template <> __device__ __forceinline__ float g_rcp_pos<float>(float x) {
+  float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+template <> __device__ __forceinline__ double g_rcp_pos<double>(double x) {
+  double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return fma(r, fma(-x, r, 1.0), r);
+}
+#endif
 #ifndef GMR_EMULATE
 template <> __device__ __forceinline__ float g_sqrt<float>(float x) { return sqrtf(x); }
 template <> __device__ __forceinline__ float g_rsqrt<float>(float x) { return rsqrtf(x); }
@@ -279,6 +300,9 @@ template <typename R> GMR_FN void m3_skew(const R* v, R* S) {
   S[0] = R(0); S[1] = -v[2]; S[2] = v[1]; S[3] = v[2]; S[4] = R(0); S[5] = -v[0]; S[6] = -v[1]; S[7] = v[0]; S[8] = R(0);
 }
 
+// lane e < 21 owns entry (r, c) of the packed upper triangle of the base block, lanes 21..26 its right-hand side
+GMR_HD constexpr int gmr_schur_r(int e) { return e < 21 ? (e >= 6) + (e >= 11) + (e >= 15) + (e >= 18) + (e >= 20) : (e < 27 ? e - 21 : 0); }
+GMR_HD constexpr int gmr_schur_c(int e, int o_y) { return e < 21 ? gmr_schur_r(e) + e - (gmr_schur_r(e) * (13 - gmr_schur_r(e))) / 2 : (e < 27 ? o_y : 0); }
 // index of (i,j) in the packed upper triangle of a symmetric 6x6 (21 entries)
 GMR_HD constexpr int gmr_sym6(int i, int j) { return i <= j ? (i * (13 - i)) / 2 + (j - i) : (j * (13 - j)) / 2 + (i - j); }
 
@@ -307,6 +331,8 @@ struct WarpSolver {
   LaneRegs<R> lanes_;
   int lane_;
   int dep_;                    // hinge depth of this lane (0: lane owns no hinge)
+  uint32_t desc_;              // strict descendants of this lane's hinge
+  int sr_, sc_;                // this lane's entry of the base block (row slot, column slot)
 #endif
   int stat_refactor;           // factorisations done (uniform)
   bool convoy;                 // CTA-wide rendezvous before every factorisation (see convoy_arrive)
@@ -323,6 +349,8 @@ struct WarpSolver {
 #ifndef GMR_EMULATE
     lane_ = lane;
     dep_ = lane < d.nh ? (int)m.hdepth[lane] : 0;
+    desc_ = lane < d.nh ? m.desc_mask[lane] : 0u;
+    sr_ = gmr_schur_r(lane); sc_ = gmr_schur_c(lane, d.o_y);
     sm_off = smem_byte_off;
 #else
     sm = smem;
@@ -370,33 +398,31 @@ struct WarpSolver {
         s_sc()[2 * lane] = s; s_sc()[2 * lane + 1] = c;
       }
       if (lane == 0) {
+        s_sc()[2 * dm.nh] = R(0); s_sc()[2 * dm.nh + 1] = R(1);          // the "hinge" of fixed bodies
         R q[4] = {s_q()[3], s_q()[4], s_q()[5], s_q()[6]};
         q_normalize(q);
-        s_xq()[0] = q[0]; s_xq()[1] = q[1]; s_xq()[2] = q[2]; s_xq()[3] = q[3];
-        s_xp()[0] = R(0); s_xp()[1] = R(0); s_xp()[2] = R(0);
-        R* rq = s_rq();
-        rq[0] = q[0]; rq[1] = q[1]; rq[2] = q[2]; rq[3] = q[3];
+        g_st4(s_xq(), q[0], q[1], q[2], q[3]);
+        g_st4(s_xp(), R(0), R(0), R(0), R(0));
+        g_st4(s_rq(), q[0], q[1], q[2], q[3]);
       }
     GMR_END
     for (int l = 1; l < dm.nlevel; l++) {
       const int beg = mc.lvl_off[l], cnt = mc.lvl_off[l + 1] - beg;
       GMR_LANES
-        for (int e = lane; e < cnt; e += 32) {
-          const int b = mc.lvl_body[beg + e], p = mc.parent[b];
-          R pq[4]; g_ld4(s_xq() + 4 * p, pq);
-          R off[3]; q_rot(pq, mc.bpos + 3 * b, off);
-          s_xp()[3 * b] = s_xp()[3 * p] + off[0]; s_xp()[3 * b + 1] = s_xp()[3 * p + 1] + off[1]; s_xp()[3 * b + 2] = s_xp()[3 * p + 2] + off[2];
-          R q[4]; q_mul(pq, mc.bquat + 4 * b, q);
-          const int j = mc.bhinge[b];
-          if (j >= 0) {
-            const R s = s_sc()[2 * j], c = s_sc()[2 * j + 1];
-            R ql[4] = {c, mc.axis[3 * j] * s, mc.axis[3 * j + 1] * s, mc.axis[3 * j + 2] * s};
-            R t[4]; q_mul(q, ql, t); q[0] = t[0]; q[1] = t[1]; q[2] = t[2]; q[3] = t[3];
-          }
+        for (int e = beg + lane; e < beg + cnt; e += 32) {
+          const uint32_t ix = mc.fk_idx[e];
+          const int b = ix & 0xffu, p = (ix >> 8) & 0xffu, j = ix >> 16;
+          R pq[4], pp[4], bp[4], A[4], B[4];
+          g_ld4(s_xq() + 4 * p, pq); g_ld4(s_xp() + 4 * p, pp);
+          g_ld4(mc.fk_pos + 4 * e, bp); g_ld4(mc.fk_A + 4 * e, A); g_ld4(mc.fk_B + 4 * e, B);
+          const R sn = s_sc()[2 * j], cs = s_sc()[2 * j + 1];
+          R off[3]; q_rot(pq, bp, off);
+          g_st4(s_xp() + 4 * b, pp[0] + off[0], pp[1] + off[1], pp[2] + off[2], R(0));
+          R ql[4] = {cs * A[0] + sn * B[0], cs * A[1] + sn * B[1], cs * A[2] + sn * B[2], cs * A[3] + sn * B[3]};
+          R q[4]; q_mul(pq, ql, q);
           // first-order renormalisation (|q| is 1 up to rounding): q *= 1.5 - 0.5 |q|^2
           const R k = R(1.5) - R(0.5) * (q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-          R* o = s_xq() + 4 * b;
-          o[0] = q[0] * k; o[1] = q[1] * k; o[2] = q[2] * k; o[3] = q[3] * k;
+          g_st4(s_xq() + 4 * b, q[0] * k, q[1] * k, q[2] * k, q[3] * k);
         }
       GMR_END
     }
@@ -405,11 +431,11 @@ struct WarpSolver {
         const int b = mc.hbody[lane];
         R q[4]; g_ld4(s_xq() + 4 * b, q);
         R w[3]; q_rot(q, mc.axis + 3 * lane, w);
-        const R* d = s_xp() + 3 * b;
+        R d[4]; g_ld4(s_xp() + 4 * b, d);
         R* o = s_sd() + 8 * lane;
         // linear velocity of the reference point (root origin) under unit joint rate: w x (0 - d) = d x w
-        o[0] = d[1] * w[2] - d[2] * w[1]; o[1] = d[2] * w[0] - d[0] * w[2]; o[2] = d[0] * w[1] - d[1] * w[0];
-        o[3] = w[0]; o[4] = w[1]; o[5] = w[2]; o[6] = R(0); o[7] = R(0);
+        g_st4(o, d[1] * w[2] - d[2] * w[1], d[2] * w[0] - d[0] * w[2], d[0] * w[1] - d[1] * w[0], w[0]);
+        g_st4(o + 4, w[1], w[2], R(0), R(0));
       }
     GMR_END
   }
@@ -468,7 +494,7 @@ struct WarpSolver {
         const int b = mc.tbody[lane], h = mc.thuman[lane];
         const R* tg = s_tg() + 8 * h;
         R qb[4]; g_ld4(s_xq() + 4 * b, qb);
-        R d[3] = {s_xp()[3 * b], s_xp()[3 * b + 1], s_xp()[3 * b + 2]};
+        R d[4]; g_ld4(s_xp() + 4 * b, d);
         R rho[3], om[3], P[9], K[9];
         R th2;
         {
@@ -736,26 +762,31 @@ struct WarpSolver {
   // the published rows and solved densely; the back substitution walks the depths root -> leaves.
   // For G1: 10 depths instead of 29 sequential pivots, rows of <= 16 slots instead of 35.
   GMR_FN void factor_solve(bool pinned_any) {
+    // per-lane constants of this factorisation: my descendants, my entry (r, cc) of the base block
+    // (lanes 0..20: packed upper triangle; lanes 21..26: the right-hand side, "column" o_y)
+    GMR_LANES
+      L.sacc = R(0);
+    GMR_END_NOSYNC
     for (int lv = dm.maxd; lv >= 1; lv--) {
-      const int beg = mc.hl_off[lv], end = mc.hl_off[lv + 1];
       const int nchunk = (5 + lv + 3) >> 2;                     // slots [0, 5 + lv) = base + strict ancestors
       GMR_LANES
         if (GMR_DEPTH == lv) {
-          const R di = R(1) / L.dg;
+          const R di = g_rcp_pos(L.dg);
           L.dinv = di;
           R* o = s_L() + dm.rs * lane;
           publish_row(o, L, R(1), nchunk);
           g_st4(o + dm.o_y, L.rhs, di, R(0), R(0));
         }
       GMR_END
-      for (int e = beg; e < end; e++) {
-        const int k = mc.hl_hinge[e];
-        const uint32_t am = mc.anc_mask[k];
+      uint32_t rem = mc.lvl_mask[lv];
+      while (rem) {
+        const int k = GMR_CTZ(rem);
+        rem &= rem - 1u;
         GMR_LANES
-          if ((am >> lane) & 1u) {
-            const R* pk = s_L() + dm.rs * k;
+          const R* pk = s_L() + dm.rs * k;
+          const R yk = pk[dm.o_y], dk = pk[dm.o_y + 1];
+          if ((GMR_DESC >> k) & 1u) {
             const R hki = pk[5 + GMR_DEPTH];
-            const R yk = pk[dm.o_y], dk = pk[dm.o_y + 1];
             const R a = hki * dk;
             GMR_UNROLL
             for (int c = 0; c < GMR_NS / 4; c++) {
@@ -767,32 +798,18 @@ struct WarpSolver {
             L.dg -= a * hki;
             L.rhs -= a * yk;
           }
+          // base block: S = A_bb - sum_k (1/d_k) h_k h_k^T,  b = b_b - sum_k (1/d_k) h_k y_k,  h_k = base slots of row k
+          if (lane < 27) L.sacc += pk[GMR_SR] * dk * pk[GMR_SC];
         GMR_END_NOSYNC
       }
     }
-    GMR_SYNC();
-    // base block: S = A_bb - sum_k (1/d_k) h_k h_k^T,  b = b_b - sum_k (1/d_k) h_k y_k,  h_k = published base slots
     GMR_LANES
       if (lane < 27) {
-        int r, cc;
-        if (lane < 21) {
-          r = (lane >= 6) + (lane >= 11) + (lane >= 15) + (lane >= 18) + (lane >= 20);
-          cc = r + lane - (r * (13 - r)) / 2;
-        } else { r = lane - 21; cc = dm.o_y; }
-        R acc0 = R(0), acc1 = R(0);
-        int k = 0;
-        for (; k + 1 < dm.nh; k += 2) {
-          const R* p0 = s_L() + dm.rs * k;
-          const R* p1 = p0 + dm.rs;
-          acc0 += p0[r] * p0[dm.o_y + 1] * p0[cc];
-          acc1 += p1[r] * p1[dm.o_y + 1] * p1[cc];
-        }
-        if (k < dm.nh) { const R* p0 = s_L() + dm.rs * k; acc0 += p0[r] * p0[dm.o_y + 1] * p0[cc]; }
         const R* rt = s_root();
         R v;
-        if (lane < 21) v = rt[lane] + ((cc == r) ? ks.damping + rt[27] : R(0));
-        else v = -rt[lane] - (pinned_any ? s_xs()[r] : R(0));
-        s_lf()[lane] = v - (acc0 + acc1);
+        if (lane < 21) v = rt[lane] + ((GMR_SC == GMR_SR) ? ks.damping + rt[27] : R(0));
+        else v = -rt[lane] - (pinned_any ? s_xs()[GMR_SR] : R(0));
+        s_lf()[lane] = v - L.sacc;
       }
     GMR_END
     // dense 6x6 solve by lane 0: S = Lf Lf^T, x_b = Lf^-T Lf^-1 b

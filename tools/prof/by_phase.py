@@ -39,6 +39,7 @@ hdr = rows[1]; col = {h: i for i, h in enumerate(hdr)}
 base = None
 agg = collections.defaultdict(lambda: collections.Counter())
 ops = collections.defaultdict(lambda: collections.Counter())
+lines = collections.defaultdict(lambda: collections.Counter())
 for r in rows[2:]:
     if len(r) < len(hdr): continue
     a = int(r[col["Address"]], 16)
@@ -55,6 +56,7 @@ for r in rows[2:]:
         if k in col: agg[f][k] += int(r[col[k]])
     op = re.sub(r"^@!?U?P\d\s+", "", text).split()[0].split(".")[0]
     ops[f][op] += ie
+    lines[(fn.split("/")[-1], ln)]["inst"] += ie; lines[(fn.split("/")[-1], ln)]["samples"] += int(r[col["# Samples"]]); lines[(fn.split("/")[-1], ln)]["static"] += 1
 tot = sum(v["inst"] for v in agg.values()); tots = sum(v["samples"] for v in agg.values())
 print(f"{'phase':18s} {'static':>6s} {'inst%':>6s} {'lanes':>5s} {'smp%':>6s}  barrier no_inst long_sb short_sb wait  mio  math notsel sel  branch")
 for f, v in sorted(agg.items(), key=lambda kv: -kv[1]["inst"]):
@@ -62,6 +64,12 @@ for f, v in sorted(agg.items(), key=lambda kv: -kv[1]["inst"]):
     print(f"{f:18s} {v['static']:6d} {100*v['inst']/tot:6.2f} {v['thr']/max(v['inst'],1):5.1f} {100*v['samples']/tots:6.2f}  " +
           " ".join(f"{100*v[k]/s:5.1f}" for k in ("stall_barrier", "stall_no_inst", "stall_long_sb", "stall_short_sb", "stall_wait", "stall_mio", "stall_math", "stall_not_selected", "stall_selected", "stall_branch_resolving")))
 print("total inst", tot, "samples", tots)
-if len(sys.argv) > 4:
+if len(sys.argv) > 4 and sys.argv[4] == "--lines":
+    lo, hi = int(sys.argv[5]), int(sys.argv[6])
+    src = open(SRC).read().split("\n")
+    for (fn, ln), v in sorted(lines.items()):
+        if fn.endswith("gmr_solver.cuh") and lo <= ln <= hi and v["inst"]:
+            print(f"{ln:5d} {v['static']:4d} {100*v['inst']/tot:6.2f}% {100*v['samples']/tots:6.2f}%  {src[ln-1][:110]}")
+elif len(sys.argv) > 4:
     for f in sys.argv[4:]:
         print(f, ops[f].most_common(25))

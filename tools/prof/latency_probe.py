@@ -40,6 +40,9 @@ for prec in ("f32", "f64"):
     slots = 148 * (28 if prec == "f32" else 14)
     run("lone_warp_one_clip_per_sm", base.pos[:148], base.quat[:148], base.heights[:148], prec)
     rep = lambda x, n: np.repeat(x[:1], n, axis=0)
+    run("lone_warp_same_clip", rep(base.pos, 148), rep(base.quat, 148), rep(base.heights, 148), prec)
+    for w in (2, 4, 8, 16):
+        run("same_clip_%d_warps_per_sm" % w, rep(base.pos, 148 * w), rep(base.quat, 148 * w), rep(base.heights, 148 * w), prec)
     run("balanced_all_slots_same_clip", rep(base.pos, slots), rep(base.quat, slots), rep(base.heights, slots), prec)
     run("balanced_2x_slots_same_clip", rep(base.pos, 2 * slots), rep(base.quat, 2 * slots), rep(base.heights, 2 * slots), prec)
     run("benchmark_mix_4096", base.pos, base.quat, base.heights, prec)
