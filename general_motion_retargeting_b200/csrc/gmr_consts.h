@@ -2,13 +2,14 @@
 // kernel stages into shared memory once per CTA.  Filled on the host by
 // gmr_fill_consts() from a GmrModelDesc (include/gmr_b200.h).
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/gmr_b200.h"
 
 #define GMR_NH 32            // lanes of a warp = hinge DoFs (GMR_MAX_HINGE)
 #define GMR_MAX_LEVEL 64
-#define GMR_MAXD 14          // deepest chain of hinges root -> leaf the factorisation is unrolled for
+#define GMR_MAXD 10          // deepest chain of hinges root -> leaf the factorisation is unrolled for (G1: 10)
 #define GMR_NS (6 + GMR_MAXD) // row slots of one hinge: 6 floating-base columns, then its ancestors by depth
 
 template <typename R>
@@ -27,6 +28,13 @@ struct GmrConsts {
   uint32_t anc_mask[GMR_NH];          // hinge i -> bitmask of hinges that are strict ancestors of i
   uint32_t desc_mask[GMR_NH];         // hinge i -> bitmask of hinges that are strict descendants of i
   uint32_t task_mask[GMR_NH];         // hinge i -> bitmask of tasks whose body lies in i's subtree
+  uint32_t top_mask[GMR_NH];          // ... restricted to tasks whose parent task is outside i's subtree
+  uint32_t troot_mask, _pad3[3];      // tasks without a parent task
+  int8_t tpar[GMR_MAX_TASK];          // task -> nearest task on a strict ancestor body (task tree), -1 if none
+  // leaf-to-root accumulation of the task tree in rounds of 4 independent (child, parent) pairs:
+  // tround[4 r + q] = child | parent << 8; 0xffff = unused slot
+  int32_t ntround, _pad4[3];
+  uint16_t tround[GMR_MAX_TASK * 4];
   int32_t maxd, tlmax, _pad2[2];      // deepest hinge chain; most tasks in any hinge's subtree
   uint32_t lvl_mask[GMR_MAXD + 2];    // [d] -> bitmask of the hinges of depth d (1-based)
   uint8_t hdepth[GMR_NH];             // hinge i -> number of hinges on the chain root .. i (inclusive); 0 for unused lanes
@@ -178,7 +186,46 @@ inline int gmr_fill_consts(const GmrModelDesc* d, GmrConsts<R>* c, const char** 
     if (d->task_in2[t]) m.in2_mask |= 1u << t;
     for (int bb = b; bb >= 0; bb = m.parent[bb]) if (m.bhinge[bb] >= 0) m.task_mask[m.bhinge[bb]] |= 1u << t;
   }
+  // task tree: the composite of a hinge is the sum of the task-subtree composites of its "top" tasks
+  for (int t = 0; t < m.nt; t++) {
+    int best = -1;
+    for (int bb = m.tbody[t]; bb >= 0 && best < 0; bb = m.parent[bb]) {
+      for (int u = 0; u < m.nt; u++) {
+        if (u == t) continue;
+        // a task on the same body counts as an ancestor only if it comes first (keeps the relation acyclic)
+        if (m.tbody[u] == bb && (bb != m.tbody[t] || u < t)) { best = u; break; }
+      }
+    }
+    m.tpar[t] = (int8_t)best;
+    if (best < 0) m.troot_mask |= 1u << t;
+  }
+  { // list scheduling: a pair (t -> tpar[t]) is ready once every child of t has been added into t; a round takes
+    // up to 4 ready pairs with distinct parents
+    int pending[GMR_MAX_TASK];                      // children not yet accumulated into t
+    bool done[GMR_MAX_TASK];
+    for (int t = 0; t < m.nt; t++) { pending[t] = 0; done[t] = m.tpar[t] < 0; }
+    for (int t = 0; t < m.nt; t++) if (m.tpar[t] >= 0) pending[m.tpar[t]]++;
+    int left = 0;
+    for (int t = 0; t < m.nt; t++) if (!done[t]) left++;
+    m.ntround = 0;
+    while (left > 0) {
+      int q = 0, chosen[4];
+      uint32_t parents_used = 0;
+      for (int t = 0; t < m.nt && q < 4; t++)
+        if (!done[t] && pending[t] == 0 && !((parents_used >> m.tpar[t]) & 1u)) { chosen[q++] = t; parents_used |= 1u << m.tpar[t]; }
+      if (q == 0) return fail(GMR_EINVAL, "task tree is cyclic");
+      for (int i = 0; i < 4; i++)
+        m.tround[4 * m.ntround + i] = i < q ? (uint16_t)(chosen[i] | (m.tpar[chosen[i]] << 8)) : (uint16_t)0xffffu;
+      for (int i = 0; i < q; i++) { done[chosen[i]] = true; pending[m.tpar[chosen[i]]]--; left--; }
+      m.ntround++;
+    }
+  }
   m.tlmax = 0;
-  for (int j = 0; j < m.nh; j++) { int n = 0; for (int t = 0; t < m.nt; t++) n += (m.task_mask[j] >> t) & 1u; if (n > m.tlmax) m.tlmax = n; }
+  for (int j = 0; j < m.nh; j++) {
+    int n = 0;
+    for (int t = 0; t < m.nt; t++)
+      if (((m.task_mask[j] >> t) & 1u) && (m.tpar[t] < 0 || !((m.task_mask[j] >> m.tpar[t]) & 1u))) { m.top_mask[j] |= 1u << t; n++; }
+    if (n > m.tlmax) m.tlmax = n;
+  }
   return GMR_OK;
 }

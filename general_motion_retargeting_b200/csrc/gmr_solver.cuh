@@ -105,7 +105,7 @@ template <typename R> GMR_HD int gmr_in_elems(int nhum) { return gmr_pad4((int)(
 //   [ mt: task inertias, max(28 nt, 72) | xp: 4 nb | xq: 4 nb ]          while FK / task evaluation are live, and
 //   [ published factor rows, nh * stride ]                                  from the factorisation to the next FK.
 // (body poses are dead once the composites are built; integrate() takes the root quaternion from GS_RQ.)
-GMR_HD constexpr int gmr_mt_elems(int nt) { return gmr_pad4(28 * nt > 72 ? 28 * nt : 72); }   // >= 2 (GMR_NH + 1) + pad for the FK sin/cos table
+GMR_HD constexpr int gmr_mt_elems(int nt) { return gmr_pad4(28 * nt > 72 ? 28 * nt : 72); }   // >= 2 (GMR_NH + 1) for the FK sin/cos table
 template <typename R> GMR_HD int gmr_warp_elems(int nb, int nh, int nhum, int nt, int maxd) {
   int u = gmr_mt_elems(nt) + 4 * nb + 4 * nb;
   const int lr = (nh > 0 ? nh : 1) * gmr_row_stride(maxd);
@@ -623,22 +623,47 @@ struct WarpSolver {
   // whole-tree composite for the floating base, per-hinge composite -> f_i = Ic_i s_i,
   // c_i = s_i . G_i, diag_i = s_i . f_i + damping + sum mu
   GMR_FN void composites() {
+    // task-subtree composites in place (children before parents; lane e owns element e of every block, so
+    // there is no cross-lane hazard), then the whole-tree composite = sum over the root tasks
+    // lane = (pair q, 128-bit chunk c) of a round: 4 pairs x 7 chunks
+    for (int r = 0; r < mc.ntround; r++) {
+      GMR_LANES
+        if (lane < 28) {
+          const int q = lane / 7, c = lane - 7 * q;
+          const uint32_t tp = mc.tround[4 * r + q];
+          if (tp != 0xffffu) {                               // unused slot of the round
+            R* dst = s_mt() + 28 * (tp >> 8) + 4 * c;
+            R a[4], b[4];
+            g_ld4(s_mt() + 28 * (tp & 0xffu) + 4 * c, a); g_ld4(dst, b);
+            g_st4(dst, a[0] + b[0], a[1] + b[1], a[2] + b[2], a[3] + b[3]);
+          }
+        }
+      GMR_END
+    }
     GMR_LANES
       if (lane < 28) {
         R s = R(0);
-        for (int t = 0; t < dm.nt; t++) s += s_mt()[28 * t + lane];
+        uint32_t rm = mc.troot_mask;
+        while (rm) { const int t = GMR_CTZ(rm); rm &= rm - 1u; s += s_mt()[28 * t + lane]; }
         s_root()[lane] = s;
       }
     GMR_END
     GMR_LANES
       if (lane < dm.nh) {
         R acc[28];
-        GMR_UNROLL
-        for (int i = 0; i < 28; i++) acc[i] = R(0);
-        // every lane walks its OWN list of subtree tasks (set bits of its mask); the trip count is the
-        // longest list of the robot, not the number of tasks
-        uint32_t tm = mc.task_mask[lane];
-        for (int it = 0; it < dm.tlmax; it++) {
+        // every lane sums the task-subtree composites of its OWN top tasks (set bits of its mask; one for
+        // most hinges of a humanoid); the trip count is the longest such list of the robot
+        uint32_t tm = mc.top_mask[lane];
+        if (tm) {                                            // the first (usually only) one is a plain load
+          const R* m = s_mt() + 28 * GMR_CTZ(tm);
+          tm &= tm - 1u;
+          GMR_UNROLL
+          for (int c = 0; c < 7; c++) g_ld4(m + 4 * c, acc + 4 * c);
+        } else {
+          GMR_UNROLL
+          for (int i = 0; i < 28; i++) acc[i] = R(0);
+        }
+        for (int it = 1; it < dm.tlmax; it++) {
           if (tm) {
             const int t = GMR_CTZ(tm);
             tm &= tm - 1u;
@@ -749,6 +774,42 @@ struct WarpSolver {
     GMR_END
   }
 
+  // one depth of the elimination: the hinges of depth lv publish their rows, their ancestors absorb them
+  template <int NCH>
+  GMR_FN void eliminate_depth(int lv) {
+    GMR_LANES
+      if (GMR_DEPTH == lv) {
+        const R di = g_rcp_pos(L.dg);
+        L.dinv = di;
+        R* o = s_L() + dm.rs * lane;
+        publish_row(o, L, R(1), NCH);
+        g_st4(o + dm.o_y, L.rhs, di, R(0), R(0));
+      }
+    GMR_END
+    uint32_t rem = mc.lvl_mask[lv];
+    while (rem) {
+      const int k = GMR_CTZ(rem);
+      rem &= rem - 1u;
+      GMR_LANES
+        const R* pk = s_L() + dm.rs * k;
+        const R yk = pk[dm.o_y], dk = pk[dm.o_y + 1];
+        if ((GMR_DESC >> k) & 1u) {
+          const R hki = pk[5 + GMR_DEPTH];
+          const R a = hki * dk;
+          GMR_UNROLL
+          for (int c = 0; c < NCH; c++) {
+            R v[4]; g_ld4(pk + 4 * c, v);
+            L.row[4 * c] -= a * v[0]; L.row[4 * c + 1] -= a * v[1]; L.row[4 * c + 2] -= a * v[2]; L.row[4 * c + 3] -= a * v[3];
+          }
+          L.dg -= a * hki;
+          L.rhs -= a * yk;
+        }
+        // base block: S = A_bb - sum_k (1/d_k) h_k h_k^T,  b = b_b - sum_k (1/d_k) h_k y_k,  h_k = base slots of row k
+        if (lane < 27) L.sacc += pk[GMR_SR] * dk * pk[GMR_SC];
+      GMR_END_NOSYNC
+    }
+  }
+
   // ------------------------------------------------------------------ factor + solve --------
   // Solves H x = rhs for the rows built above; result in s_xs[0..nv) (base first).
   //
@@ -768,39 +829,12 @@ struct WarpSolver {
       L.sacc = R(0);
     GMR_END_NOSYNC
     for (int lv = dm.maxd; lv >= 1; lv--) {
-      const int nchunk = (5 + lv + 3) >> 2;                     // slots [0, 5 + lv) = base + strict ancestors
-      GMR_LANES
-        if (GMR_DEPTH == lv) {
-          const R di = g_rcp_pos(L.dg);
-          L.dinv = di;
-          R* o = s_L() + dm.rs * lane;
-          publish_row(o, L, R(1), nchunk);
-          g_st4(o + dm.o_y, L.rhs, di, R(0), R(0));
-        }
-      GMR_END
-      uint32_t rem = mc.lvl_mask[lv];
-      while (rem) {
-        const int k = GMR_CTZ(rem);
-        rem &= rem - 1u;
-        GMR_LANES
-          const R* pk = s_L() + dm.rs * k;
-          const R yk = pk[dm.o_y], dk = pk[dm.o_y + 1];
-          if ((GMR_DESC >> k) & 1u) {
-            const R hki = pk[5 + GMR_DEPTH];
-            const R a = hki * dk;
-            GMR_UNROLL
-            for (int c = 0; c < GMR_NS / 4; c++) {
-              if (c < nchunk) {
-                R v[4]; g_ld4(pk + 4 * c, v);
-                L.row[4 * c] -= a * v[0]; L.row[4 * c + 1] -= a * v[1]; L.row[4 * c + 2] -= a * v[2]; L.row[4 * c + 3] -= a * v[3];
-              }
-            }
-            L.dg -= a * hki;
-            L.rhs -= a * yk;
-          }
-          // base block: S = A_bb - sum_k (1/d_k) h_k h_k^T,  b = b_b - sum_k (1/d_k) h_k y_k,  h_k = base slots of row k
-          if (lane < 27) L.sacc += pk[GMR_SR] * dk * pk[GMR_SC];
-        GMR_END_NOSYNC
+      // slots [0, 5 + lv) = base + strict ancestors; the chunk count is a template argument so that shallow
+      // depths do not issue (predicated-off) work for slots they do not have
+      switch ((5 + lv + 3) >> 2) {
+        case 2: eliminate_depth<2>(lv); break;
+        case 3: eliminate_depth<3>(lv); break;
+        default: eliminate_depth<GMR_NS / 4>(lv); break;
       }
     }
     GMR_LANES
