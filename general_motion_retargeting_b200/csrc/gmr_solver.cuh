@@ -337,7 +337,9 @@ struct WarpSolver {
   int stat_refactor;           // factorisations done (uniform)
   bool convoy;                 // CTA-wide rendezvous before every factorisation (see convoy_arrive)
   volatile int* cta_active;    // shared count of warps that still have clips (convoy mode)
-  uint32_t warm_lo, warm_hi;   // working set carried from the previous solve (uniform)
+  // working set carried from the previous solve of the same STAGE (uniform).  Four scalars, selected by
+  // comparison: a dynamically indexed member array would push the whole solver object into local memory.
+  uint32_t warm_lo0, warm_hi0, warm_lo1, warm_hi1;
 
 #ifdef GMR_EMULATE
   GMR_FN WarpSolver(const GmrConsts<R>& m, const GmrDims& d, const GmrScal<R>& k, R* smem)
@@ -345,7 +347,7 @@ struct WarpSolver {
   // smem_byte_off: offset of this warp's state block from the start of the dynamic shared window
   GMR_FN WarpSolver(const GmrConsts<R>& m, const GmrDims& d, const GmrScal<R>& k, uint32_t smem_byte_off, int lane)
 #endif
-                     : mc(m), dm(d), ks(k), stat_refactor(0), convoy(false), cta_active(nullptr), warm_lo(0), warm_hi(0) {
+                     : mc(m), dm(d), ks(k), stat_refactor(0), convoy(false), cta_active(nullptr), warm_lo0(0), warm_hi0(0), warm_lo1(0), warm_hi1(0) {
 #ifndef GMR_EMULATE
     lane_ = lane;
     dep_ = lane < d.nh ? (int)m.hdepth[lane] : 0;
@@ -917,22 +919,25 @@ struct WarpSolver {
   // The step is left in s_xs[0..nv).  One code instance of build_rows/factor_solve: the loop
   // alternates between SOLVE passes and (only when bounds are pinned) a CHECK pass that
   // evaluates the KKT multipliers on the original rows.
-  GMR_FN void solve_qp() {
+  GMR_FN void solve_qp(int stage) {
     const R INF = R(INFINITY);
+    const uint32_t w_lo = stage == 0 ? warm_lo0 : warm_lo1, w_hi = stage == 0 ? warm_hi0 : warm_hi1;
     GMR_LANES
       if (lane < dm.nh) {
-        // feasible start: bounds that were active at the end of the previous solve stay in the
-        // working set (their joints sit on, or creep towards, the limit), everything else at
-        // clip(0, lo, hi).  Any feasible start gives the same (unique) optimum.
+        // feasible start: bounds that were active at the end of the previous solve of this stage stay in
+        // the working set (their joints sit on, or creep towards, the limit), everything else at
+        // clip(0, lo, hi).  Any feasible start gives the same (unique) optimum.  The two stages weigh the
+        // tasks differently and settle on different working sets, so each keeps its own.
         const R bhi = bound_hi(lane), blo = bound_lo(lane);
         R x;
-        if ((warm_hi >> lane) & 1u) x = bhi;
-        else if ((warm_lo >> lane) & 1u) x = blo;
+        if ((w_hi >> lane) & 1u) x = bhi;
+        else if ((w_lo >> lane) & 1u) x = blo;
         else x = R(0) < blo ? blo : (R(0) > bhi ? bhi : R(0));
         lp(LP_X, lane) = x;
       }
     GMR_END
-    uint32_t pin_lo = warm_lo & dm.limited_mask, pin_hi = warm_hi & dm.limited_mask;
+    uint32_t pin_lo = w_lo & dm.limited_mask, pin_hi = w_hi & dm.limited_mask;
+    int nchecks = 0;
     bool check = false;
     const int max_as = 8 * dm.nh + 16;
     for (int it = 0; it < max_as; it++) {
@@ -1028,12 +1033,19 @@ struct WarpSolver {
         if (g_abs(l) > gmax) gmax = g_abs(l);
         if (worst < 0 || l < lmin) { lmin = l; worst = j; }
       }
+      if (worst < 0 || lmin >= -GmrEps<R>::lam * gmax) { GMR_SYNC(); break; }
+      // release: the first two checks of a solve drop EVERY bound with a multiplier of the wrong sign (a
+      // stage switch typically flips several at once), later ones only the worst (the textbook rule, which
+      // cannot cycle).  Whatever the path, the loop only ends on a point that passes this KKT check.
+      uint32_t drop = 1u << worst;
+      if (nchecks < 2)
+        for (int j = 0; j < dm.nh; j++) if (((pinned >> j) & 1u) && s_red()[j] < -GmrEps<R>::lam * gmax) drop |= 1u << j;
+      nchecks++;
       GMR_SYNC();
-      if (worst < 0 || lmin >= -GmrEps<R>::lam * gmax) break;
-      pin_lo &= ~(1u << worst); pin_hi &= ~(1u << worst);
+      pin_lo &= ~drop; pin_hi &= ~drop;
       check = false;
     }
-    warm_lo = pin_lo; warm_hi = pin_hi;
+    if (stage == 0) { warm_lo0 = pin_lo; warm_hi0 = pin_hi; } else { warm_lo1 = pin_lo; warm_hi1 = pin_hi; }
     // publish the final step (hinge part) for integration
     GMR_LANES
       if (lane < dm.nh) s_xs()[6 + lane] = lp(LP_X, lane);
@@ -1143,7 +1155,7 @@ struct WarpSolver {
   GMR_FN void run_clip(const float* pos, const float* quat, R ratio, int T, const IO* qinit, IO* qpos_out,
                        int32_t* iters_out, IO* err_out, IO* tg_out, uint32_t flags) {
     if (qinit) set_qpos(qinit); else set_qpos(mc.qpos0);
-    warm_lo = warm_hi = 0;
+    warm_lo0 = warm_lo1 = warm_hi0 = warm_hi1 = 0;
     if (T <= 0) return;
     stage_frame(pos, quat);
     const int first_stage = dm.use1 ? 0 : 1;
@@ -1181,7 +1193,7 @@ struct WarpSolver {
       }
       if (solve) {
         composites();
-        solve_qp();
+        solve_qp(stage);
         integrate();
         need_fk = true;
         nsolve++;
