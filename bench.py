@@ -146,7 +146,7 @@ def main_reference(args):
     from general_motion_retargeting_b200.synthetic import make_clips
     robot, table = load_problem(args)
     cores = os.cpu_count() or 1
-    sample = max(8 * cores, 64)          # enough clips per thread that the tail does not dominate
+    sample = max(32 * cores, 64)         # a few seconds of CPU work per step; enough clips per thread that the tail does not dominate
     clips = make_clips(robot, table, range(sample), T=args.frames, src_human=args.src)
     for _ in range(max(args.warmup, 0)):
         cpu_reference_run(robot, table, clips)
@@ -296,7 +296,7 @@ def main_ours(args):
     cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = min(C, max(8 * cores, 64))
+        sample = min(C, max(64 * cores, 64))      # ~10 s of CPU work on the box's host cores
         sub = type(clips)(pos=clips.pos[:sample], quat=clips.quat[:sample], heights=clips.heights[:sample],
                           qpos_gen=clips.qpos_gen[:sample])
         q_ref, it_ref, dt = cpu_reference_run(robot, table, sub)
@@ -326,6 +326,17 @@ def main_ours(args):
         achieved_tf = flops_step / (kernel_ms_avg * 1e-3) / 1e12
         s1, s2 = flop_model(robot, table)
         bytes_step = C * T * (table.nh * 7 + robot.nq) * 4
+        # DRAM bytes of one launch of this exact configuration from an `ncu --set full` capture
+        # (profiles/traffic.json, written by tools/prof/summarize.py); None when no capture matches
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                for rec in json.load(f):
+                    if (rec["robot"], rec["src"], rec["clips"], rec["frames"], rec["precision"]) == \
+                            (args.robot, args.src, C, T, args.precision):
+                        traffic, traffic_src = rec["dram_bytes_per_launch"], rec["source"]
+        except Exception:
+            pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         line = {
             "metric": "retargeted frames/sec (G1 29-DoF)", "value": value, "unit": "frames/s",
@@ -342,7 +353,7 @@ def main_ours(args):
             "e2e": e2e,
             "roofline": {"bound": "fp32_fma" if args.precision == "f32" else "fp64_fma",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                         "traffic": None,
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "peak_basis": f"{nsm} SMs x {lanes} lanes x 2 x {sm_max:.0f} MHz (nominal at max clock; "
                                        f"median clock observed under load {sm_obs:.0f} MHz)",
                          "flops_per_step": flops_step, "kernel_ms": kernel_ms_avg,

@@ -483,65 +483,85 @@ struct WarpSolver {
   }
 
   // ------------------------------------------------------------------ tasks (A7, A9, A10) ---
-  // Per task: error e = log(T_b^-1 T_t) = (rho, omega) -> s_red[t] = |e|^2 (unweighted, all
-  // tasks); P = Jinv(omega) R_b^T;  K' = -Jinv Q Jinv R_b^T - P [d_b]x (the position rows'
-  // dependence on rotation, shifted to the root origin); then with the stage's weights
-  // s_mt[t] = M_t packed upper (21) | g_t (6) | mu_t, where
+  // Split in two so that the work a stage decision does not need is not done:
+  //   task_error()      e = log(T_b^-1 T_t) = (rho, omega) per task -> s_red[t] = |e|^2 (unweighted, all tasks);
+  //                     the lane keeps (omega, rho, theta^2, |v|^2, cos(theta/2), cV) and the body pose it used.
+  //   task_build(stage) only when an IK step follows: P = Jinv(omega) R_b^T;  K' = -Jinv Q Jinv R_b^T - P [d_b]x
+  //                     (the position rows' dependence on rotation, shifted to the root origin); then with the
+  //                     stage's weights s_mt[t] = M_t packed upper (21) | g_t (6) | mu_t, where
   //   M = [[wp2 P^T P, wp2 P^T K'], [., wp2 K'^T K' + wr2 P^T P]],
   //   g = A'^T W e = -[wp2 P^T rho ; wp2 K'^T rho + wr2 P^T omega],  mu = lm (wp2 |rho|^2 + wr2 |omega|^2).
-  GMR_FN void task_eval(int stage) {
-    const uint32_t stage_mask = stage == 0 ? dm.in1_mask : dm.in2_mask;
+  // Per frame that is (solves + stages) error evaluations but only (solves) builds, and a stage switch
+  // re-sums the same |e_t|^2 with the other stage's task mask instead of re-evaluating anything.
+  GMR_FN void task_error() {
     GMR_LANES
       if (lane < dm.nt) {
         const int b = mc.tbody[lane], h = mc.thuman[lane];
         const R* tg = s_tg() + 8 * h;
         R qb[4]; g_ld4(s_xq() + 4 * b, qb);
         R d[4]; g_ld4(s_xp() + 4 * b, d);
-        R rho[3], om[3], P[9], K[9];
-        R th2;
+        R qi[4] = {qb[0], -qb[1], -qb[2], -qb[3]};
+        R qt[4]; g_ld4(tg + 4, qt);
+        R qe[4]; q_mul(qi, qt, qe);
+        if (qe[0] < R(0)) { qe[0] = -qe[0]; qe[1] = -qe[1]; qe[2] = -qe[2]; qe[3] = -qe[3]; }
+        // world offset target - body, via root-relative coordinates
+        R dw[3] = {(tg[0] - s_q()[0]) - d[0], (tg[1] - s_q()[1]) - d[1], (tg[2] - s_q()[2]) - d[2]};
+        R tb[3]; q_rot_inv(qb, dw, tb);
+        // SO(3) log
+        const R nsq = qe[1] * qe[1] + qe[2] * qe[2] + qe[3] * qe[3];
+        R fac;
+        if (nsq < GmrEps<R>::lie) fac = R(2) / qe[0] - R(2) / R(3) * nsq / (qe[0] * qe[0] * qe[0]);
+        else { const R n = g_sqrt(nsq); fac = R(2) * g_atan2(n, qe[0]) / n; }
+        R om[3] = {fac * qe[1], fac * qe[2], fac * qe[3]};
+        const R th2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
+        // Jinv = I - S/2 + cV S^2, cV = (1 - (theta/2) cot(theta/2)) / theta^2 (also V^-1 of SE3.log)
+        R cV;
+        if (th2 < GmrEps<R>::lie) cV = R(1) / R(12);
+        else if (th2 < R(0.0625)) cV = R(1) / R(12) + th2 * (R(1) / R(720) + th2 * (R(1) / R(30240) + th2 / R(1209600)));   // series: the closed form cancels badly for small theta
+        else cV = (R(1) - R(0.5) * g_sqrt(th2) * qe[0] / g_sqrt(nsq)) / th2;
+        // rho = Jinv tb = tb - (omega x tb) / 2 + cV omega x (omega x tb)
+        R c1[3] = {om[1] * tb[2] - om[2] * tb[1], om[2] * tb[0] - om[0] * tb[2], om[0] * tb[1] - om[1] * tb[0]};
+        R c2[3] = {om[1] * c1[2] - om[2] * c1[1], om[2] * c1[0] - om[0] * c1[2], om[0] * c1[1] - om[1] * c1[0]};
+        R rho[3] = {tb[0] - R(0.5) * c1[0] + cV * c2[0], tb[1] - R(0.5) * c1[1] + cV * c2[1], tb[2] - R(0.5) * c1[2] + cV * c2[2]};
+        s_red()[lane] = rho[0] * rho[0] + rho[1] * rho[1] + rho[2] * rho[2] + th2;
+        // hand-over to task_build(): parked in the task's own (still unused) M_t block rather than in registers
+        R* o = s_mt() + 28 * lane;
+        g_st4(o, om[0], om[1], om[2], th2); g_st4(o + 4, rho[0], rho[1], rho[2], nsq);
+        g_st4(o + 8, d[0], d[1], d[2], qe[0]); g_st4(o + 12, qb[0], qb[1], qb[2], qb[3]);
+        o[16] = cV;
+      }
+    GMR_END
+  }
+
+  GMR_FN void task_build(int stage) {
+    const uint32_t stage_mask = stage == 0 ? dm.in1_mask : dm.in2_mask;
+    GMR_LANES
+      if (lane < dm.nt) {
+        R om[4], rho[4], d[4], qb[4], P[9], K[9];
+        const R* in = s_mt() + 28 * lane;
+        g_ld4(in, om); g_ld4(in + 4, rho); g_ld4(in + 8, d); g_ld4(in + 12, qb);
+        const R th2 = om[3], nsq = rho[3], cw = d[3], cV = in[16];
         {
-          R qi[4] = {qb[0], -qb[1], -qb[2], -qb[3]};
-          R qt[4]; g_ld4(tg + 4, qt);
-          R qe[4]; q_mul(qi, qt, qe);
-          if (qe[0] < R(0)) { qe[0] = -qe[0]; qe[1] = -qe[1]; qe[2] = -qe[2]; qe[3] = -qe[3]; }
-          // world offset target - body, via root-relative coordinates
-          R dw[3] = {(tg[0] - s_q()[0]) - d[0], (tg[1] - s_q()[1]) - d[1], (tg[2] - s_q()[2]) - d[2]};
-          R tb[3]; q_rot_inv(qb, dw, tb);
-          // SO(3) log
-          const R nsq = qe[1] * qe[1] + qe[2] * qe[2] + qe[3] * qe[3];
-          R fac;
-          if (nsq < GmrEps<R>::lie) fac = R(2) / qe[0] - R(2) / R(3) * nsq / (qe[0] * qe[0] * qe[0]);
-          else { const R n = g_sqrt(nsq); fac = R(2) * g_atan2(n, qe[0]) / n; }
-          om[0] = fac * qe[1]; om[1] = fac * qe[2]; om[2] = fac * qe[3];
-          th2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
-          // Jinv = I - S/2 + cV S^2, cV = (1 - (theta/2) cot(theta/2)) / theta^2 (also V^-1 of SE3.log);
           // Bq, Cq, Dq: Barfoot's Q coefficients
-          R cV, Bq, Cq, Dq;
+          R Bq, Cq, Dq;
           if (th2 < GmrEps<R>::lie) {
-            cV = R(1) / R(12); Bq = R(1) / R(6); Cq = -R(1) / R(24); Dq = R(1) / R(120);
+            Bq = R(1) / R(6); Cq = -R(1) / R(24); Dq = R(1) / R(120);
+          } else if (th2 < R(0.0625)) {                    // series: the closed forms cancel badly for small theta
+            Bq = R(1) / R(6) - th2 * (R(1) / R(120) - th2 * (R(1) / R(5040) - th2 / R(362880)));
+            Cq = -R(1) / R(24) + th2 * (R(1) / R(720) - th2 * (R(1) / R(40320) - th2 / R(3628800)));
+            Dq = R(1) / R(120) - th2 * (R(1) / R(2520) - th2 * (R(1) / R(120960) - th2 / R(9979200)));
           } else {
             const R th = g_sqrt(th2);
-            const R n = g_sqrt(nsq);                       // sin(theta/2); qe[0] = cos(theta/2)
-            if (th < R(0.25)) {                            // series: the closed forms cancel badly for small theta
-              cV = R(1) / R(12) + th2 * (R(1) / R(720) + th2 * (R(1) / R(30240) + th2 / R(1209600)));
-              Bq = R(1) / R(6) - th2 * (R(1) / R(120) - th2 * (R(1) / R(5040) - th2 / R(362880)));
-              Cq = -R(1) / R(24) + th2 * (R(1) / R(720) - th2 * (R(1) / R(40320) - th2 / R(3628800)));
-              Dq = R(1) / R(120) - th2 * (R(1) / R(2520) - th2 * (R(1) / R(120960) - th2 / R(9979200)));
-            } else {
-              cV = (R(1) - R(0.5) * th * qe[0] / n) / th2;
-              const R st = R(2) * n * qe[0], ct = qe[0] * qe[0] - nsq;
-              Bq = (th - st) / (th2 * th);
-              Cq = (R(1) - th2 * R(0.5) - ct) / (th2 * th2);
-              Dq = (R(2) * th - R(3) * st + th * ct) / (R(2) * th2 * th2 * th);
-            }
+            const R n = g_sqrt(nsq);                       // sin(theta/2); cw = cos(theta/2)
+            const R st = R(2) * n * cw, ct = cw * cw - nsq;
+            Bq = (th - st) / (th2 * th);
+            Cq = (R(1) - th2 * R(0.5) - ct) / (th2 * th2);
+            Dq = (R(2) * th - R(3) * st + th * ct) / (R(2) * th2 * th2 * th);
           }
           R S[9], S2[9], Ji[9];
           m3_skew(om, S); m3_mul(S, S, S2);
           GMR_UNROLL
           for (int i = 0; i < 9; i++) Ji[i] = ((i & 3) == 0 ? R(1) : R(0)) - R(0.5) * S[i] + cV * S2[i];
-          rho[0] = Ji[0] * tb[0] + Ji[1] * tb[1] + Ji[2] * tb[2];
-          rho[1] = Ji[3] * tb[0] + Ji[4] * tb[1] + Ji[5] * tb[2];
-          rho[2] = Ji[6] * tb[0] + Ji[7] * tb[1] + Ji[8] * tb[2];
           // Q(rho, omega) with W V W = -(omega.rho) W,  W V W W + W W V W = -2 (omega.rho) W^2
           R Q[9];
           {
@@ -573,7 +593,6 @@ struct WarpSolver {
           for (int i = 0; i < 9; i++) K[i] = -T2[i] - PS[i];
         }
         const R r2 = rho[0] * rho[0] + rho[1] * rho[1] + rho[2] * rho[2];
-        s_red()[lane] = r2 + th2;
         R* o = s_mt() + 28 * lane;
         const bool on = (stage_mask >> lane) & 1u;
         const R* wtab = stage == 0 ? mc.w1 : mc.w2;
@@ -1164,19 +1183,19 @@ struct WarpSolver {
     int n0 = 0, n1 = 0;
     R e0 = R(0), e1 = R(0);
     R curr = R(0);
-    bool frame_start = true, need_fk = true;
+    bool frame_start = true, need_fk = true, need_err = true;
     for (;;) {
       if (frame_start) {
         frame_wait();
         update_targets(ratio, (flags & GMR_FLAG_OFFSET_TO_GROUND) != 0);
         if (t + 1 < T) stage_frame(pos + (size_t)(t + 1) * dm.nhum * 3, quat + (size_t)(t + 1) * dm.nhum * 4);
         stage = first_stage; nsolve = 0; n0 = n1 = 0; e0 = e1 = R(0);
-        frame_start = false;
+        frame_start = false; need_err = true;
       }
-      if (need_fk) { fk(); need_fk = false; }
+      if (need_fk) { fk(); need_fk = false; need_err = true; }
       bool solve = false, done = !any_stage;
       if (any_stage) {
-        task_eval(stage);
+        if (need_err) { task_error(); need_err = false; }     // a stage switch re-sums the same |e_t|^2 with the other mask
         const R e = stage_error(stage);
         if (flags & GMR_FLAG_NO_SOLVE) {                 // targets + errors only (update_targets / error1 / error2)
           if (stage == 0) e0 = e; else e1 = e;
@@ -1192,6 +1211,7 @@ struct WarpSolver {
         }
       }
       if (solve) {
+        task_build(stage);
         composites();
         solve_qp(stage);
         integrate();
