@@ -218,6 +218,7 @@ def main_ours(args):
     iters = it_info.cpu().numpy()
     flops_step = flops_of_run(robot, table, iters)
     q_gpu_sample = q_info[: min(C, 4096)].double().cpu().numpy()
+    out_elem_bytes = q_info.element_size()      # float64 qpos from the float64 kernel, float32 from the float32 one
     del q_info, it_info
 
     for _ in range(args.warmup):
@@ -325,7 +326,7 @@ def main_ours(args):
         peak_tf = nsm * lanes * 2 * sm_max * 1e6 / 1e12
         achieved_tf = flops_step / (kernel_ms_avg * 1e-3) / 1e12
         s1, s2 = flop_model(robot, table)
-        bytes_step = C * T * (table.nh * 7 + robot.nq) * 4
+        bytes_step = C * T * (table.nh * 7 * 4 + robot.nq * out_elem_bytes)
         # DRAM bytes of one launch of this exact configuration from an `ncu --set full` capture
         # (profiles/traffic.json, written by tools/prof/summarize.py); None when no capture matches
         traffic, traffic_src = None, None
