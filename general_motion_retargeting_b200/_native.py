@@ -90,6 +90,12 @@ def build_desc(robot: RobotModel, table: TaskTable, damping: float = 0.5, lm_dam
     return d, keep
 
 
+class GmrBatchExtra(C.Structure):
+    """Mirror of the C struct (device pointers as integers; 0 = NULL)."""
+    _fields_ = [("lengths", C.c_void_p), ("local_body_pos", C.c_void_p), ("lowest_z", C.c_void_p),
+                ("warm_state", C.c_void_p)]
+
+
 class NativeLibraryMissing(RuntimeError):
     pass
 
@@ -122,6 +128,20 @@ def load_library() -> C.CDLL:
     lib.gmr_retarget_batch_host.argtypes = [vp, f32p, f32p, f32p, C.c_int32, C.c_int32, f32p, f32p, i32p, f32p,
                                             C.c_uint32]
     lib.gmr_retarget_batch_host.restype = C.c_int
+    lib.gmr_retarget_batch_ex.argtypes = [vp, f32p, f32p, f32p, C.c_int32, C.c_int32, f32p, f32p, i32p, f32p, f32p,
+                                          C.POINTER(GmrBatchExtra), C.c_uint32, vp]
+    lib.gmr_retarget_batch_ex.restype = C.c_int
+    lib.gmr_finalize_motion.argtypes = [vp, f32p, f32p, i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        f32p, f32p, f32p, vp]
+    lib.gmr_finalize_motion.restype = C.c_int
+    lib.gmr_stream_create.argtypes = [vp, C.c_double, C.POINTER(vp)]
+    lib.gmr_stream_create.restype = C.c_int
+    lib.gmr_stream_destroy.argtypes = [vp]
+    lib.gmr_stream_destroy.restype = C.c_int
+    lib.gmr_stream_reset.argtypes = [vp, vp]
+    lib.gmr_stream_reset.restype = C.c_int
+    lib.gmr_stream_retarget.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, vp, vp]
+    lib.gmr_stream_retarget.restype = C.c_int
     lib.gmr_launch_count.argtypes = []
     lib.gmr_launch_count.restype = C.c_int64
     lib.gmr_last_error.argtypes = []
@@ -135,4 +155,6 @@ def load_library() -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "gmr_model_create", "gmr_model_destroy", "gmr_retarget_batch", "gmr_retarget_batch_f64",
     "gmr_retarget_batch_host", "gmr_launch_count", "gmr_last_error", "gmr_kernel_info",
+    "gmr_retarget_batch_ex", "gmr_finalize_motion",
+    "gmr_stream_create", "gmr_stream_destroy", "gmr_stream_reset", "gmr_stream_retarget",
 ]

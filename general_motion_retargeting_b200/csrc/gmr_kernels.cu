@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -65,7 +66,7 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
                     const GmrConsts<R>* __restrict__ gconsts, const float* __restrict__ pos, const float* __restrict__ quat,
                     const float* __restrict__ ratio, int C, int T, const IO* __restrict__ qinit, IO* __restrict__ qout,
                     int32_t* __restrict__ iters, IO* __restrict__ err, IO* __restrict__ tg, uint32_t flags,
-                    int* __restrict__ queue) {
+                    int* __restrict__ queue, const __grid_constant__ GmrBatchExtra ex) {
   extern __shared__ __align__(128) unsigned char gmr_dyn_smem[];
   unsigned char* const smem = gmr_dyn_smem;
   constexpr int CB = consts_bytes<R>();
@@ -89,15 +90,46 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
   const int nw = gridDim.x * wpc;
   for (int c = warp * gridDim.x + blockIdx.x; c < C;) {
     const size_t f0 = (size_t)c * T;
-    ws.template run_clip<IO>(pos + f0 * nhum * 3, quat + f0 * nhum * 4, ratio ? R(ratio[c]) : R(1), T,
+    int Tc = T;                                                       // ragged batch: this clip's own length
+    if (ex.lengths) { Tc = ex.lengths[c]; Tc = Tc < 0 ? 0 : (Tc > T ? T : Tc); }
+    ws.template run_clip<IO>(pos + f0 * nhum * 3, quat + f0 * nhum * 4, ratio ? R(ratio[c]) : R(1), Tc,
                              qinit ? qinit + (size_t)c * nq : nullptr, qout + f0 * nq,
                              iters ? iters + 2 * f0 : nullptr, err ? err + 2 * f0 : nullptr,
-                             tg ? tg + f0 * nhum * 7 : nullptr, flags);
+                             tg ? tg + f0 * nhum * 7 : nullptr, flags,
+                             ex.local_body_pos ? ex.local_body_pos + f0 * dm.nb * 3 : nullptr,
+                             ex.lowest_z ? ex.lowest_z + c : nullptr, ex.warm_state ? ex.warm_state + 4 * c : nullptr);
     int nxt = 0;
     if (lane == 0) nxt = nw + atomicAdd(queue, 1);
     c = __shfl_sync(0xffffffffu, nxt, 0);
   }
   ws.convoy_retire();
+}
+
+// Motion-file epilogue (gmr_finalize_motion): one thread per (clip, frame, qpos element).  HBM-bound elementwise
+// pass: reads qpos once (4 nq bytes per frame, coalesced), writes the three arrays of the pkl once.
+__global__ void __launch_bounds__(256)
+gmr_finalize_kernel(const float* __restrict__ qpos, const float* __restrict__ lowest, const int32_t* __restrict__ lengths,
+                    int C, int T, int nq, int height_adjust, int origin_offset,
+                    float* __restrict__ root_pos, float* __restrict__ root_rot, float* __restrict__ dof_pos) {
+  const size_t n = (size_t)C * T * nq;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t f = i / nq;                 // frame index c * T + t
+    const int e = (int)(i - f * nq);
+    const int c = (int)(f / T), t = (int)(f - (size_t)c * T);
+    const bool live = !lengths || t < lengths[c];
+    float v = live ? qpos[i] : 0.0f;
+    if (e < 3) {
+      if (live) {
+        if (e == 2) { if (height_adjust && lowest) v -= lowest[c]; }
+        else if (origin_offset) v -= qpos[(size_t)c * T * nq + e];          // first frame of the clip
+      }
+      root_pos[f * 3 + e] = v;
+    } else if (e < 7) {
+      root_rot[f * 4 + (e == 3 ? 3 : e - 4)] = v;                           // wxyz -> xyzw
+    } else {
+      dof_pos[f * (nq - 7) + (e - 7)] = v;
+    }
+  }
 }
 
 constexpr int QUEUE_RING = 256;
@@ -167,8 +199,11 @@ template <typename R> int pick_wpc(const GmrModel* m, int C) {
 
 template <typename R, typename IO, int MAXWARPS>
 int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* quat, const float* ratio, int C, int T,
-           const IO* qinit, IO* qout, int32_t* iters, IO* err, IO* tg, uint32_t flags, cudaStream_t st) {
+           const IO* qinit, IO* qout, int32_t* iters, IO* err, IO* tg, uint32_t flags, cudaStream_t st,
+           const GmrBatchExtra* extra = nullptr, int* own_queue = nullptr) {
   if (C == 0 || T == 0) return GMR_OK;
+  GmrBatchExtra ex{};
+  if (extra) ex = *extra;
   auto kern = gmr_retarget_kernel<R, IO, MAXWARPS>;
   const int wpc = pick_wpc<R>(m, C);
   const size_t smem = smem_bytes<R>(m, wpc);
@@ -186,9 +221,9 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
   static const int cv_env = getenv("GMR_CONVOY") ? atoi(getenv("GMR_CONVOY")) : 0;
   const bool convoy = cv_env != 0 && wpc >= 2;
   flags = (flags & 0xffffu) | (convoy ? GMR_FLAG_INTERNAL_CONVOY : 0u);
-  int* queue = m->d_queue + (m->queue_next.fetch_add(1) % QUEUE_RING);
+  int* queue = own_queue ? own_queue : m->d_queue + (m->queue_next.fetch_add(1) % QUEUE_RING);
   CK(cudaMemsetAsync(queue, 0, sizeof(int), st));
-  kern<<<grid, wpc * 32, smem, st>>>(sizeof(R) == 4 ? m->dims32 : m->dims64, scal_of<R>(m), dc, pos, quat, ratio, C, T, qinit, qout, iters, err, tg, flags, queue);
+  kern<<<grid, wpc * 32, smem, st>>>(sizeof(R) == 4 ? m->dims32 : m->dims64, scal_of<R>(m), dc, pos, quat, ratio, C, T, qinit, qout, iters, err, tg, flags, queue, ex);
   g_launches.fetch_add(1);
   CK(cudaGetLastError());
   return GMR_OK;
@@ -272,6 +307,185 @@ int gmr_retarget_batch(GmrModel* m, const float* pos, const float* quat, const f
                                            targets_out, flags, (cudaStream_t)cuda_stream);
   return launch<float, float, MAXW_F32>(m, m->d_f32, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out,
                                         targets_out, flags, (cudaStream_t)cuda_stream);
+}
+
+int gmr_retarget_batch_ex(GmrModel* m, const float* pos, const float* quat, const float* ratio, int32_t C, int32_t T,
+                          const float* qpos_init, float* qpos_out, int32_t* iters_out, float* err_out, float* targets_out,
+                          const GmrBatchExtra* extra, uint32_t flags, void* cuda_stream) {
+  if (!m) return set_err(GMR_EINVAL, "model is null");
+  if (C < 0 || T < 0) return set_err(GMR_EINVAL, "negative batch size");
+  if ((C > 0 && T > 0) && (!pos || !quat || !qpos_out)) return set_err(GMR_EINVAL, "pos, quat and qpos_out are required");
+  if ((reinterpret_cast<uintptr_t>(quat) & 15u) != 0) return set_err(GMR_EINVAL, "quat must be 16-byte aligned");
+  DeviceGuard g(m->device);
+  if (!g.ok) return set_err(GMR_ECUDA, "cannot select the model's device");
+  if (flags & GMR_FLAG_COMPUTE_F64)
+    return launch<double, float, MAXW_F64>(m, m->d_f64, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out,
+                                           targets_out, flags, (cudaStream_t)cuda_stream, extra);
+  return launch<float, float, MAXW_F32>(m, m->d_f32, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out,
+                                        targets_out, flags, (cudaStream_t)cuda_stream, extra);
+}
+
+int gmr_finalize_motion(GmrModel* m, const float* qpos, const float* lowest_z, const int32_t* lengths, int32_t C, int32_t T,
+                        int32_t height_adjust, int32_t origin_offset, float* root_pos_out, float* root_rot_xyzw_out,
+                        float* dof_pos_out, void* cuda_stream) {
+  if (!m) return set_err(GMR_EINVAL, "model is null");
+  if (C < 0 || T < 0) return set_err(GMR_EINVAL, "negative batch size");
+  if (C == 0 || T == 0) return GMR_OK;
+  if (!qpos || !root_pos_out || !root_rot_xyzw_out || (m->h_f32.nh > 0 && !dof_pos_out))
+    return set_err(GMR_EINVAL, "qpos and the three output arrays are required");
+  DeviceGuard g(m->device);
+  if (!g.ok) return set_err(GMR_ECUDA, "cannot select the model's device");
+  const size_t n = (size_t)C * T * m->h_f32.nq;
+  size_t blocks = (n + 255) / 256;
+  const size_t cap = (size_t)m->num_sms * 16;             // grid-stride: a multiple of the SM count
+  if (blocks > cap) blocks = cap;
+  gmr_finalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(
+      qpos, lowest_z, lengths, C, T, m->h_f32.nq, height_adjust, origin_offset, root_pos_out, root_rot_xyzw_out, dof_pos_out);
+  g_launches.fetch_add(1);
+  CK(cudaGetLastError());
+  return GMR_OK;
+}
+
+// ---- single live stream ---------------------------------------------------------------------------------
+}  // extern "C"
+
+struct GmrStream {
+  GmrModel* m = nullptr;
+  cudaStream_t st = nullptr;
+  char* h_in = nullptr;    // pinned: pos [nh,3] f32 | quat [nh,4] f32 (16-byte aligned) | ratio f32
+  char* h_out = nullptr;   // pinned: qpos [nq] f64 | err [2] f64 | targets [nh,7] f64 | iters [2] i32
+  char* d_buf = nullptr;   // device: the same two blocks, then the state: qpos [nq] f64 | working sets [4] u32
+  size_t in_bytes = 0, out_bytes = 0, o_quat = 0, o_ratio = 0, o_err = 0, o_tg = 0, o_it = 0, o_state = 0, o_warm = 0;
+  cudaGraphExec_t graph[4] = {nullptr, nullptr, nullptr, nullptr};      // by (flags & 3)
+  bool graph_failed = false;
+  std::mutex mu;
+};
+
+namespace {
+inline size_t up16(size_t b) { return (b + 15) & ~(size_t)15; }
+
+// copy in -> solve (one clip, one frame, float64) -> keep the new configuration -> copy out, on s->st
+int stream_enqueue(GmrStream* s, uint32_t flags) {
+  GmrModel* m = s->m;
+  char* d = s->d_buf;
+  CK(cudaMemcpyAsync(d, s->h_in, s->in_bytes, cudaMemcpyHostToDevice, s->st));
+  char* dout = d + up16(s->in_bytes);
+  GmrBatchExtra ex{};
+  ex.warm_state = (flags & GMR_FLAG_NO_SOLVE) ? nullptr : reinterpret_cast<uint32_t*>(d + s->o_warm);
+  int rc = launch<double, double, MAXW_F64>(m, m->d_f64, (const float*)d, (const float*)(d + s->o_quat), (const float*)(d + s->o_ratio), 1, 1,
+                                            (const double*)(d + s->o_state), (double*)dout, (int32_t*)(dout + s->o_it),
+                                            (double*)(dout + s->o_err), (double*)(dout + s->o_tg), flags & 3u, s->st, &ex,
+                                            reinterpret_cast<int*>(d + s->o_warm + 16));
+  if (rc != GMR_OK) return rc;
+  if (!(flags & GMR_FLAG_NO_SOLVE))
+    CK(cudaMemcpyAsync(d + s->o_state, dout, (size_t)m->h_f32.nq * 8, cudaMemcpyDeviceToDevice, s->st));
+  CK(cudaMemcpyAsync(s->h_out, dout, s->out_bytes, cudaMemcpyDeviceToHost, s->st));
+  return GMR_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int gmr_stream_create(GmrModel* m, double height_ratio, GmrStream** out) {
+  if (!out) return set_err(GMR_EINVAL, "out is null");
+  *out = nullptr;
+  if (!m) return set_err(GMR_EINVAL, "model is null");
+  DeviceGuard g(m->device);
+  if (!g.ok) return set_err(GMR_ECUDA, "cannot select the model's device");
+  GmrStream* s = new (std::nothrow) GmrStream();
+  if (!s) return set_err(GMR_ENOMEM, "host allocation failed");
+  s->m = m;
+  const size_t nh = m->h_f32.nhum, nq = m->h_f32.nq;
+  s->o_quat = up16(nh * 3 * 4); s->o_ratio = s->o_quat + nh * 4 * 4; s->in_bytes = s->o_ratio + 16;
+  s->o_err = up16(nq * 8); s->o_tg = s->o_err + 16; s->o_it = s->o_tg + up16(nh * 7 * 8); s->out_bytes = s->o_it + 16;
+  s->o_state = up16(s->in_bytes) + up16(s->out_bytes); s->o_warm = s->o_state + up16(nq * 8);
+  cudaError_t e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMallocHost(&s->h_in, s->in_bytes);
+  if (e == cudaSuccess) e = cudaMallocHost(&s->h_out, s->out_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_buf, s->o_warm + 32);          // + working sets + this stream's own clip-queue counter
+  if (e == cudaSuccess) e = cudaMemset(s->d_buf, 0, s->o_warm + 32);
+  if (e != cudaSuccess) { int code = cuda_err(e, "gmr_stream_create"); gmr_stream_destroy(s); return code; }
+  *reinterpret_cast<float*>(s->h_in + s->o_ratio) = (float)height_ratio;
+  int rc = gmr_stream_reset(s, nullptr);
+  if (rc != GMR_OK) { gmr_stream_destroy(s); return rc; }
+  *out = s;
+  return GMR_OK;
+}
+
+int gmr_stream_destroy(GmrStream* s) {
+  if (!s) return GMR_OK;
+  DeviceGuard g(s->m->device);
+  if (s->st) cudaStreamSynchronize(s->st);
+  for (auto& ge : s->graph) if (ge) cudaGraphExecDestroy(ge);
+  if (s->d_buf) cudaFree(s->d_buf);
+  if (s->h_in) cudaFreeHost(s->h_in);
+  if (s->h_out) cudaFreeHost(s->h_out);
+  if (s->st) cudaStreamDestroy(s->st);
+  (void)cudaGetLastError();
+  delete s;
+  return GMR_OK;
+}
+
+int gmr_stream_reset(GmrStream* s, const double* qpos) {
+  if (!s) return set_err(GMR_EINVAL, "stream is null");
+  DeviceGuard g(s->m->device);
+  if (!g.ok) return set_err(GMR_ECUDA, "cannot select the model's device");
+  std::lock_guard<std::mutex> lk(s->mu);
+  const int nq = s->m->h_f32.nq;
+  std::vector<double> q(nq);
+  for (int i = 0; i < nq; i++) q[i] = qpos ? qpos[i] : (double)s->m->h_f32.qpos0[i];
+  if (!qpos) {                       // qpos0 in full precision comes from the float64 constant block on the device
+    CK(cudaMemcpyAsync(s->d_buf + s->o_state, reinterpret_cast<const char*>(s->m->d_f64) + offsetof(GmrConsts<double>, qpos0),
+                       (size_t)nq * 8, cudaMemcpyDeviceToDevice, s->st));
+  } else {
+    CK(cudaMemcpyAsync(s->d_buf + s->o_state, q.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, s->st));
+  }
+  CK(cudaMemsetAsync(s->d_buf + s->o_warm, 0, 16, s->st));
+  CK(cudaStreamSynchronize(s->st));
+  return GMR_OK;
+}
+
+int gmr_stream_retarget(GmrStream* s, const float* pos, const float* quat, uint32_t flags, double* qpos_out,
+                        int32_t* iters_out, double* err_out, double* targets_out) {
+  if (!s) return set_err(GMR_EINVAL, "stream is null");
+  if (!pos || !quat || !qpos_out) return set_err(GMR_EINVAL, "pos, quat and qpos_out are required");
+  GmrModel* m = s->m;
+  DeviceGuard g(m->device);
+  if (!g.ok) return set_err(GMR_ECUDA, "cannot select the model's device");
+  std::lock_guard<std::mutex> lk(s->mu);
+  const size_t nh = m->h_f32.nhum, nq = m->h_f32.nq;
+  memcpy(s->h_in, pos, nh * 3 * 4);
+  memcpy(s->h_in + s->o_quat, quat, nh * 4 * 4);
+  const uint32_t f = flags & 3u;
+  if (!s->graph[f] && !s->graph_failed) {
+    // first call with these flags: run once eagerly (also opts the kernel into its shared-memory size), then
+    // capture the same sequence for every later frame
+    int rc = stream_enqueue(s, f);
+    if (rc != GMR_OK) return rc;
+    CK(cudaStreamSynchronize(s->st));
+    cudaGraph_t gr = nullptr;
+    bool ok = cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      ok = stream_enqueue(s, f) == GMR_OK;                  // recorded, not executed
+      cudaError_t e = cudaStreamEndCapture(s->st, &gr);
+      ok = ok && e == cudaSuccess && gr;
+    }
+    if (ok) ok = cudaGraphInstantiate(&s->graph[f], gr, 0) == cudaSuccess;
+    if (gr) cudaGraphDestroy(gr);
+    if (!ok) { s->graph[f] = nullptr; s->graph_failed = true; (void)cudaGetLastError(); }
+  } else if (s->graph[f]) {
+    CK(cudaGraphLaunch(s->graph[f], s->st));
+    CK(cudaStreamSynchronize(s->st));
+  } else {
+    int rc = stream_enqueue(s, f);
+    if (rc != GMR_OK) return rc;
+    CK(cudaStreamSynchronize(s->st));
+  }
+  memcpy(qpos_out, s->h_out, nq * 8);
+  if (err_out) memcpy(err_out, s->h_out + s->o_err, 16);
+  if (targets_out) memcpy(targets_out, s->h_out + s->o_tg, nh * 7 * 8);
+  if (iters_out) memcpy(iters_out, s->h_out + s->o_it, 8);
+  return GMR_OK;
 }
 
 int gmr_retarget_batch_f64(GmrModel* m, const float* pos, const float* quat, const float* ratio, int32_t C, int32_t T,

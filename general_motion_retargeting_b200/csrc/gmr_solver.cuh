@@ -1172,9 +1172,17 @@ struct WarpSolver {
   //               while curr - next > tol and n < max_iter: curr = next; solve; next = err(); n += 1
   template <typename IO>
   GMR_FN void run_clip(const float* pos, const float* quat, R ratio, int T, const IO* qinit, IO* qpos_out,
-                       int32_t* iters_out, IO* err_out, IO* tg_out, uint32_t flags) {
+                       int32_t* iters_out, IO* err_out, IO* tg_out, uint32_t flags,
+                       float* lbp_out = nullptr, float* lowest_out = nullptr, uint32_t* warm_io = nullptr) {
+    // post-solve epilogue of the dataset scripts (scripts/smplx_to_robot_dataset.py:93-123), fused: the last FK
+    // of a frame is the FK of the frame's answer, so
+    //   lbp_out [T,nb,3]  local_body_pos = FK with an identity root = R_root^T (x_b - x_root), and
+    //   lowest_out [1]    min over frames and bodies of the world z (the height adjustment of :118-123)
+    // cost one pass over the body poses already in shared memory.
+    R lowest = R(INFINITY);
     if (qinit) set_qpos(qinit); else set_qpos(mc.qpos0);
     warm_lo0 = warm_lo1 = warm_hi0 = warm_hi1 = 0;
+    if (warm_io) { warm_lo0 = warm_io[0]; warm_hi0 = warm_io[1]; warm_lo1 = warm_io[2]; warm_hi1 = warm_io[3]; }
     if (T <= 0) return;
     stage_frame(pos, quat);
     const int first_stage = dm.use1 ? 0 : 1;
@@ -1233,10 +1241,45 @@ struct WarpSolver {
             o[0] = IO(g[0]); o[1] = IO(g[1]); o[2] = IO(g[2]); o[3] = IO(g[4]); o[4] = IO(g[5]); o[5] = IO(g[6]); o[6] = IO(g[7]);
           }
         GMR_END
+        if (lbp_out || lowest_out) {
+          GMR_LANES
+            R zmin = R(INFINITY);
+            R rq[4]; g_ld4(s_rq(), rq);
+            for (int b = lane; b < dm.nb; b += 32) {
+              R v[4]; g_ld4(s_xp() + 4 * b, v);
+              if (v[2] < zmin) zmin = v[2];
+              if (lbp_out) {
+                R o[3]; q_rot_inv(rq, v, o);
+                float* dst = lbp_out + ((size_t)t * dm.nb + b) * 3;
+                dst[0] = (float)o[0]; dst[1] = (float)o[1]; dst[2] = (float)o[2];
+              }
+            }
+            s_red()[lane] = zmin;
+          GMR_END
+#ifdef GMR_EMULATE
+          R zm = s_red()[0];
+          for (int j = 1; j < 32; j++) { const R z = s_red()[j]; if (z < zm) zm = z; }
+#else
+          R zm = s_red()[lane_];
+          GMR_UNROLL
+          for (int o = 16; o > 0; o >>= 1) { const R z = __shfl_xor_sync(0xffffffffu, zm, o); if (z < zm) zm = z; }
+#endif
+          zm += s_q()[2];
+          if (zm < lowest) lowest = zm;
+          GMR_SYNC();
+        }
         t++;
         if (t == T) break;
         frame_start = true;
       }
+    }
+    if (lowest_out || warm_io) {
+      GMR_LANES
+        if (lane == 0) {
+          if (lowest_out) *lowest_out = (float)lowest;
+          if (warm_io) { warm_io[0] = warm_lo0; warm_io[1] = warm_hi0; warm_io[2] = warm_lo1; warm_io[3] = warm_hi1; }
+        }
+      GMR_END
     }
   }
 };

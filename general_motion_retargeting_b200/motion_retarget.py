@@ -57,6 +57,24 @@ class _Handle:
             pass
 
 
+class _Stream:
+    """One gmr_stream_create() handle: the persistent configuration of a live retargeter."""
+
+    def __init__(self, lib, handle: _Handle, ratio: float):
+        self.lib, self.handle = lib, handle          # keeps the model handle alive
+        self.ptr = C.c_void_p()
+        rc = lib.gmr_stream_create(handle.ptr, float(ratio), C.byref(self.ptr))
+        if rc != 0:
+            raise RuntimeError(f"gmr_stream_create failed ({rc}): {lib.gmr_last_error().decode()}")
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.gmr_stream_destroy(self.ptr)
+        except Exception:
+            pass
+
+
 class GeneralMotionRetargeting:
     """General Motion Retargeting (GMR), B200-native solve."""
 
@@ -115,6 +133,8 @@ class GeneralMotionRetargeting:
 
         self._lib = _native.load_library()          # raises NativeLibraryMissing: no CPU fallback
         self._handles: Dict[int, _Handle] = {}
+        self._stream: Optional[_Stream] = None
+        self._stream_qpos: Optional[np.ndarray] = None
         self._device = self._resolve_device(device)
 
         self.setup_retarget_configuration()
@@ -143,6 +163,7 @@ class GeneralMotionRetargeting:
         return h
 
     def _invalidate_handles(self) -> None:
+        self._stream = None
         self._handles = {}
 
     def _check(self, rc: int, what: str) -> None:
@@ -172,31 +193,26 @@ class GeneralMotionRetargeting:
         return pos, quat
 
     def _run_single(self, pos: np.ndarray, quat: np.ndarray, flags: int):
-        """One frame through the device entry (float64 or float32 kernel) with the persistent state."""
-        import torch
-        dev = torch.device("cuda", self._device)
-        h = self._handle(self._device)
-        f64 = self.precision == "f64"
-        dt = torch.float64 if f64 else torch.float32
+        """One frame through the live-stream entry (gmr_stream_retarget): the configuration and the solver's
+        working sets stay on the device between calls, one captured CUDA graph launch per frame (float64)."""
         nq, nh = self._robot.nq, self._table.nh
-        with torch.cuda.device(dev):
-            d_pos = torch.from_numpy(pos).to(dev)
-            d_quat = torch.from_numpy(quat).to(dev)
-            d_ratio = torch.tensor([self._ratio], dtype=torch.float32, device=dev)
-            d_init = torch.from_numpy(self._qpos.reshape(1, nq)).to(dev, dt)
-            d_q = torch.empty((1, 1, nq), dtype=dt, device=dev)
-            d_it = torch.zeros((1, 1, 2), dtype=torch.int32, device=dev)
-            d_err = torch.zeros((1, 1, 2), dtype=dt, device=dev)
-            d_tg = torch.empty((1, 1, nh, 7), dtype=dt, device=dev)
-            fn = self._lib.gmr_retarget_batch_f64 if f64 else self._lib.gmr_retarget_batch
-            rc = fn(h.ptr, d_pos.data_ptr(), d_quat.data_ptr(), d_ratio.data_ptr(), 1, 1, d_init.data_ptr(),
-                    d_q.data_ptr(), d_it.data_ptr(), d_err.data_ptr(), d_tg.data_ptr(), flags,
-                    torch.cuda.current_stream(dev).cuda_stream)
-            self._check(rc, "gmr_retarget_batch")
-            q = d_q.double().cpu().numpy()[0, 0]
-            it = d_it.cpu().numpy()[0, 0]
-            err = d_err.double().cpu().numpy()[0, 0]
-            tg = d_tg.double().cpu().numpy()[0, 0]
+        if self._stream is None:
+            self._stream = _Stream(self._lib, self._handle(self._device), self._ratio)
+            self._stream_qpos = None
+        if self._stream_qpos is None or not np.array_equal(self._stream_qpos, self._qpos):
+            # fresh instance, setup_retarget_configuration(), or the caller edited configuration.q
+            q0 = np.ascontiguousarray(self._qpos, np.float64)
+            self._check(self._lib.gmr_stream_reset(self._stream.ptr, q0.ctypes.data), "gmr_stream_reset")
+            self._stream_qpos = q0.copy()
+        q = np.empty(nq, np.float64)
+        it = np.zeros(2, np.int32)
+        err = np.zeros(2, np.float64)
+        tg = np.empty((nh, 7), np.float64)
+        rc = self._lib.gmr_stream_retarget(self._stream.ptr, pos.ctypes.data, quat.ctypes.data, flags, q.ctypes.data,
+                                           it.ctypes.data, err.ctypes.data, tg.ctypes.data)
+        self._check(rc, "gmr_stream_retarget")
+        if not (flags & FLAG_NO_SOLVE):
+            self._stream_qpos = q.copy()
         return q, it, err, tg
 
     def _store_targets(self, tg: np.ndarray) -> None:
@@ -394,3 +410,78 @@ class GeneralMotionRetargeting:
             None if iters is None else iters.ctypes.data, None if err is None else err.ctypes.data, flags)
         self._check(rc, "gmr_retarget_batch_host")
         return (qpos, iters, err) if return_info else qpos
+
+
+    # ------------------------------------------------------------------ dataset entry ---------
+    def retarget_dataset(self, pos, quat=None, heights=None, lengths=None, height_adjust: bool = True,
+                         root_origin_offset: bool = True, precision: Optional[str] = None, fps: float = 30.0,
+                         as_numpy: bool = True):
+        """What `process_file` of scripts/smplx_to_robot_dataset.py:78-146 (and bvh_to_robot_dataset.py:96-157)
+        computes for a whole batch of files in two launches: the per-frame IK (as `retarget_batch`) with the
+        post-solve forward kinematics fused in (`local_body_pos`, the clip-wide lowest body height), then one
+        elementwise pass that splits qpos into `root_pos` (height-adjusted, re-origined to the first frame),
+        `root_rot` (xyzw) and `dof_pos`.  `height_adjust`/`root_origin_offset` are the scripts' HEIGHT_ADJUST and
+        ROOT_ORIGIN_OFFSET switches (True/True in the SMPL-X script, False/False in the BVH script).
+        `lengths` [C]: frames per clip for ragged batches (padding frames are not solved).
+        Returns a list of C motion dicts in the reference's pkl layout
+        (fps, root_pos [T,3], root_rot [T,4] xyzw, dof_pos [T,ndof], local_body_pos [T,nbody,3], link_body_list)."""
+        import torch
+        if quat is None:
+            pos, quat, lengths = self.pack_clips(pos)
+        precision = precision or self.precision
+        nq, nh, nb = self._robot.nq, self._table.nh, self._robot.nbody
+        dev = pos.device if _is_torch(pos) and pos.is_cuda else torch.device("cuda", self._device)
+        h = self._handle(dev.index if dev.index is not None else torch.cuda.current_device())
+        with torch.cuda.device(dev):
+            d_pos = torch.as_tensor(pos).to(dev, torch.float32).contiguous()
+            d_quat = torch.as_tensor(quat).to(dev, torch.float32).contiguous()
+            Cn, T = int(d_pos.shape[0]), int(d_pos.shape[1])
+            if tuple(d_pos.shape[2:]) != (nh, 3) or tuple(d_quat.shape) != (Cn, T, nh, 4):
+                raise ValueError(f"expected pos [C,T,{nh},3] and quat [C,T,{nh},4]")
+            if heights is None:
+                d_ratio = torch.full((Cn,), self._ratio, dtype=torch.float32, device=dev)
+            else:
+                d_ratio = (torch.as_tensor(heights, device=dev).to(torch.float64) / float(self._cfg.human_height_assumption)).to(torch.float32).contiguous()
+            d_len = None if lengths is None else torch.as_tensor(np.asarray(lengths), device=dev).to(torch.int32).contiguous()
+            d_q = torch.zeros((Cn, T, nq), dtype=torch.float32, device=dev)
+            d_lbp = torch.zeros((Cn, T, nb, 3), dtype=torch.float32, device=dev)
+            d_low = torch.zeros((Cn,), dtype=torch.float32, device=dev)
+            ex = _native.GmrBatchExtra(None if d_len is None else d_len.data_ptr(), d_lbp.data_ptr(), d_low.data_ptr(), None)
+            st = torch.cuda.current_stream(dev).cuda_stream
+            flags = FLAG_COMPUTE_F64 if precision == "f64" else 0
+            rc = self._lib.gmr_retarget_batch_ex(h.ptr, d_pos.data_ptr(), d_quat.data_ptr(), d_ratio.data_ptr(), Cn, T, None,
+                                                 d_q.data_ptr(), None, None, None, C.byref(ex), flags, st)
+            self._check(rc, "gmr_retarget_batch_ex")
+            d_rp = torch.empty((Cn, T, 3), dtype=torch.float32, device=dev)
+            d_rr = torch.empty((Cn, T, 4), dtype=torch.float32, device=dev)
+            d_dof = torch.empty((Cn, T, nq - 7), dtype=torch.float32, device=dev)
+            rc = self._lib.gmr_finalize_motion(h.ptr, d_q.data_ptr(), d_low.data_ptr(), None if d_len is None else d_len.data_ptr(),
+                                               Cn, T, int(height_adjust), int(root_origin_offset),
+                                               d_rp.data_ptr(), d_rr.data_ptr(), d_dof.data_ptr(), st)
+            self._check(rc, "gmr_finalize_motion")
+            if not as_numpy:
+                return {"fps": fps, "root_pos": d_rp, "root_rot": d_rr, "dof_pos": d_dof, "local_body_pos": d_lbp,
+                        "lowest_z": d_low, "qpos": d_q, "link_body_list": list(self._robot.body_names), "lengths": d_len}
+            rp, rr, dof, lbp = (x.cpu().numpy() for x in (d_rp, d_rr, d_dof, d_lbp))
+        n = [T] * Cn if lengths is None else [int(x) for x in np.asarray(lengths)]
+        return [{"fps": fps, "root_pos": rp[c, :n[c]], "root_rot": rr[c, :n[c]], "dof_pos": dof[c, :n[c]],
+                 "local_body_pos": lbp[c, :n[c]], "link_body_list": list(self._robot.body_names)} for c in range(Cn)]
+
+    @staticmethod
+    def save_motion_pkls(motions: Sequence[dict], paths: Sequence[str], workers: int = 8) -> None:
+        """pickle.dump of each motion dict to its path (scripts/smplx_to_robot_dataset.py:143-146), on a
+        small thread pool: the files are independent and the work is I/O."""
+        import os
+        import pickle
+        from concurrent.futures import ThreadPoolExecutor
+
+        def one(args):
+            m, p = args
+            d = os.path.dirname(p)
+            if d:
+                os.makedirs(d, exist_ok=True)
+            with open(p, "wb") as f:
+                pickle.dump(m, f)
+
+        with ThreadPoolExecutor(max_workers=max(1, workers)) as ex:
+            list(ex.map(one, zip(motions, paths)))

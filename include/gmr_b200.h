@@ -106,6 +106,48 @@ int gmr_retarget_batch(GmrModel* model, const float* pos, const float* quat, con
                        int32_t* iters_out, float* err_out, float* targets_out,
                        uint32_t flags, void* cuda_stream);
 
+/* Optional extras of one batch (every member may be NULL): ragged clip lengths and the post-solve forward-
+ * kinematics epilogue of the dataset scripts (scripts/smplx_to_robot_dataset.py:93-123,
+ * scripts/bvh_to_robot_dataset.py:107-143), fused into the solve kernel. Device pointers. */
+typedef struct GmrBatchExtra {
+  const int32_t* lengths;     /* [C] frames of clip c (<= T); later frames are neither read nor written      */
+  float* local_body_pos;      /* [C,T,nbody,3] KinematicsModel.forward_kinematics(0, identity, dof_pos)[0]   */
+  float* lowest_z;            /* [C] min over frames and bodies of the world z (torch.min(body_pos[..., 2])) */
+  uint32_t* warm_state;       /* [C,4] in/out: the solver's working sets (joints resting on a limit) carried from
+                                 one call to the next when a clip is fed in pieces; zeros to start            */
+} GmrBatchExtra;
+
+/* gmr_retarget_batch with extras; flags may carry GMR_FLAG_COMPUTE_F64. */
+int gmr_retarget_batch_ex(GmrModel* model, const float* pos, const float* quat, const float* ratio,
+                          int32_t C, int32_t T, const float* qpos_init, float* qpos_out,
+                          int32_t* iters_out, float* err_out, float* targets_out,
+                          const GmrBatchExtra* extra, uint32_t flags, void* cuda_stream);
+
+/* The rest of the scripts' epilogue as one elementwise pass (replaces :97-131 / :112-143): splits qpos into
+ * the arrays the motion pkl holds (consumers: data_loader.py:4-16, booster_gym/utils/motion_loader.py:42-100),
+ *   root_pos [C,T,3], root_rot [C,T,4] xyzw (:103-104), dof_pos [C,T,nhinge]            (all float32, device)
+ * with, per clip, root_pos.z -= lowest_z[c] if height_adjust (:118-123) and root_pos.xy -= root_pos.xy of the
+ * clip's first frame if origin_offset (:125-128).  lengths/lowest_z may be NULL (no raggedness / no adjust). */
+int gmr_finalize_motion(GmrModel* model, const float* qpos, const float* lowest_z, const int32_t* lengths,
+                        int32_t C, int32_t T, int32_t height_adjust, int32_t origin_offset,
+                        float* root_pos_out, float* root_rot_xyzw_out, float* dof_pos_out, void* cuda_stream);
+
+/* ---- single live stream: `retargeter.retarget(frame)` once per incoming frame ------------------------------
+ * (callers: scripts/smplx_to_robot.py:125, scripts/bvh_to_robot.py:118, scripts/optitrack_to_robot.py:40).
+ * A stream owns what mink.Configuration owns in the reference (motion_retarget.py:75): the current qpos, which
+ * warm-starts the next frame, plus pinned staging buffers, a CUDA stream and a captured CUDA graph
+ * (copy in -> solve -> copy out), so one call costs one graph launch.  float64 arithmetic.  HOST pointers. */
+typedef struct GmrStream GmrStream;
+int gmr_stream_create(GmrModel* model, double height_ratio, GmrStream** out);
+int gmr_stream_destroy(GmrStream* stream);
+/* set the configuration (NULL: the model's qpos0), like constructing a fresh retargeter */
+int gmr_stream_reset(GmrStream* stream, const double* qpos);
+/* pos [nhuman,3], quat [nhuman,4] float32 -> qpos_out [nq] float64 (required); iters_out [2], err_out [2],
+ * targets_out [nhuman,7] may be NULL.  flags: GMR_FLAG_OFFSET_TO_GROUND, GMR_FLAG_NO_SOLVE (update_targets /
+ * error1 / error2: the configuration is left untouched).  Returns when qpos_out is valid. */
+int gmr_stream_retarget(GmrStream* stream, const float* pos, const float* quat, uint32_t flags,
+                        double* qpos_out, int32_t* iters_out, double* err_out, double* targets_out);
+
 /* float64 variant of the same kernel (identical semantics; qpos_init/qpos_out/err_out/
  * targets_out are double).  Exists so that parity can be checked without float32 rounding. */
 int gmr_retarget_batch_f64(GmrModel* model, const float* pos, const float* quat, const float* ratio,

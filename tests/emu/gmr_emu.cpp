@@ -12,7 +12,7 @@
 template <typename R>
 static int run(const GmrModelDesc* d, const float* pos, const float* quat, const float* ratio, int C, int T,
                const double* qpos_init, double* qpos_out, int32_t* iters_out, double* err_out, double* tg_out,
-               uint32_t flags, int nthreads, int64_t* refactor_out) {
+               uint32_t flags, int nthreads, int64_t* refactor_out, const GmrBatchExtra* ex) {
   auto* mc = new GmrConsts<R>();
   const char* why = nullptr;
   int rc = gmr_fill_consts<R>(d, mc, &why);
@@ -32,10 +32,15 @@ static int run(const GmrModelDesc* d, const float* pos, const float* quat, const
       if (c >= C) break;
       auto* ws = new WarpSolver<R>(*mc, dims, ks, sm.data());
       size_t f0 = (size_t)c * T;
-      ws->template run_clip<double>(pos + f0 * mc->nhum * 3, quat + f0 * mc->nhum * 4, ratio ? R(ratio[c]) : R(1), T,
+      int Tc = T;
+      if (ex && ex->lengths) { Tc = ex->lengths[c]; Tc = Tc < 0 ? 0 : (Tc > T ? T : Tc); }
+      ws->template run_clip<double>(pos + f0 * mc->nhum * 3, quat + f0 * mc->nhum * 4, ratio ? R(ratio[c]) : R(1), Tc,
                                     qpos_init ? qpos_init + (size_t)c * mc->nq : nullptr, qpos_out + f0 * mc->nq,
                                     iters_out ? iters_out + 2 * f0 : nullptr, err_out ? err_out + 2 * f0 : nullptr,
-                                    tg_out ? tg_out + f0 * mc->nhum * 7 : nullptr, flags);
+                                    tg_out ? tg_out + f0 * mc->nhum * 7 : nullptr, flags,
+                                    ex && ex->local_body_pos ? ex->local_body_pos + f0 * mc->nb * 3 : nullptr,
+                                    ex && ex->lowest_z ? ex->lowest_z + c : nullptr,
+                                    ex && ex->warm_state ? ex->warm_state + 4 * c : nullptr);
       refac += ws->stat_refactor;
       delete ws;
     }
@@ -54,6 +59,16 @@ extern "C" int gmr_emu_retarget_batch(const GmrModelDesc* d, const float* pos, c
                                       int32_t* iters_out, double* err_out, double* tg_out, uint32_t flags,
                                       int32_t nthreads, int32_t precision_bits, int64_t* refactor_out) {
   if (precision_bits == 32)
-    return run<float>(d, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out, tg_out, flags, nthreads, refactor_out);
-  return run<double>(d, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out, tg_out, flags, nthreads, refactor_out);
+    return run<float>(d, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out, tg_out, flags, nthreads, refactor_out, nullptr);
+  return run<double>(d, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out, tg_out, flags, nthreads, refactor_out, nullptr);
+}
+
+// same with the GmrBatchExtra members (host pointers here): ragged lengths, local body positions, lowest z
+extern "C" int gmr_emu_retarget_batch_ex(const GmrModelDesc* d, const float* pos, const float* quat, const float* ratio,
+                                         int32_t C, int32_t T, const double* qpos_init, double* qpos_out,
+                                         int32_t* iters_out, double* err_out, double* tg_out, const GmrBatchExtra* ex,
+                                         uint32_t flags, int32_t nthreads, int32_t precision_bits) {
+  if (precision_bits == 32)
+    return run<float>(d, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out, tg_out, flags, nthreads, nullptr, ex);
+  return run<double>(d, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out, tg_out, flags, nthreads, nullptr, ex);
 }

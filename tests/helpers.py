@@ -51,3 +51,40 @@ def compare(q, it, q_ref, it_ref):
     dq = np.abs(q - q_ref).max(-1)
     clean = np.logical_and.accumulate(same, axis=1)
     return float(same.mean()), float(dq.max()), float(dq[clean].max()) if clean.any() else 0.0
+
+
+def emu_retarget_batch_ex(robot, table, pos, quat, ratio, lengths=None, bits=64, flags=0, qpos_init=None, warm_state=None):
+    """Emulator with the GmrBatchExtra members: returns (qpos, iters, local_body_pos, lowest_z, warm_state)."""
+    from general_motion_retargeting_b200._native import GmrBatchExtra
+    global _emu
+    if _emu is None:
+        _emu = C.CDLL(EMU)
+        _emu.gmr_emu_retarget_batch.restype = C.c_int
+    Cn, T = pos.shape[:2]
+    desc, keep = build_desc(robot, table)
+    qpos = np.zeros((Cn, T, robot.nq)); iters = np.zeros((Cn, T, 2), np.int32)
+    lbp = np.zeros((Cn, T, robot.nbody, 3), np.float32); low = np.zeros(Cn, np.float32)
+    warm = np.zeros((Cn, 4), np.uint32) if warm_state is None else np.ascontiguousarray(warm_state, np.uint32).copy()
+    pos = np.ascontiguousarray(pos, np.float32); quat = np.ascontiguousarray(quat, np.float32)
+    ratio = np.ascontiguousarray(ratio, np.float32)
+    ln = None if lengths is None else np.ascontiguousarray(lengths, np.int32)
+    qi = None if qpos_init is None else np.ascontiguousarray(qpos_init, np.float64)
+    ex = GmrBatchExtra(None if ln is None else ln.ctypes.data, lbp.ctypes.data, low.ctypes.data, warm.ctypes.data)
+    rc = _emu.gmr_emu_retarget_batch_ex(
+        C.byref(desc), C.c_void_p(pos.ctypes.data), C.c_void_p(quat.ctypes.data), C.c_void_p(ratio.ctypes.data), Cn, T,
+        None if qi is None else C.c_void_p(qi.ctypes.data), C.c_void_p(qpos.ctypes.data), C.c_void_p(iters.ctypes.data),
+        None, None, C.byref(ex), flags, 0, bits)
+    assert rc == 0, rc
+    return qpos, iters, lbp, low, warm
+
+
+def oracle_body_positions(robot, pack, qpos):
+    """(local_body_pos [T,nb,3] = FK with an identity root, world body_pos [T,nb,3]) from the float64 oracle FK."""
+    from oracle.gmr_oracle import OracleRetargeter
+    o = OracleRetargeter(robot, pack["ik_config"])
+    T = qpos.shape[0]
+    local = np.zeros((T, robot.nbody, 3)); world = np.zeros((T, robot.nbody, 3))
+    for t in range(T):
+        o.qpos[:] = qpos[t]; o._fk(); world[t] = o.xpos
+        o.qpos[0:3] = 0.0; o.qpos[3:7] = [1.0, 0.0, 0.0, 0.0]; o._fk(); local[t] = o.xpos
+    return local, world

@@ -111,3 +111,32 @@ def test_single_stage_and_iteration_cap(built):
     clips = make_clips(m, tt, [0], T=5)
     q, it, err, _, _ = emu_retarget_batch(m, tt, clips.pos, clips.quat, clips.ratio(tt), bits=64, max_iter=0)
     assert (it == 1).all()
+
+
+def test_fk_epilogue_ragged_lengths_and_warm_state(built):
+    """GmrBatchExtra: local_body_pos / lowest_z (the dataset scripts' post-solve FK, fused), ragged clip
+    lengths, and the working-set hand-over that lets a clip be fed in pieces."""
+    from helpers import emu_retarget_batch_ex, oracle_body_positions
+    m, tt, pack = problem("smplx", "unitree_g1")
+    clips = make_clips(m, tt, [2, 3, 5], T=12)
+    ratio = clips.ratio(tt)
+    lengths = np.array([12, 7, 1], np.int32)
+    q, it, lbp, low, _ = emu_retarget_batch_ex(m, tt, clips.pos, clips.quat, ratio, lengths=lengths)
+    q_full, it_full, _, _, _ = emu_retarget_batch(m, tt, clips.pos, clips.quat, ratio, bits=64)
+    for c, n in enumerate(lengths):
+        np.testing.assert_array_equal(q[c, :n], q_full[c, :n])        # a shorter clip is a prefix of the longer one
+        assert (q[c, n:] == 0).all() and (it[c, n:] == 0).all()         # padding frames are not touched
+        local, world = oracle_body_positions(m, pack, q[c, :n])
+        np.testing.assert_allclose(lbp[c, :n], local, atol=2e-6)
+        assert abs(low[c] - world[..., 2].min()) < 2e-6
+    # with joints resting on their limits, splitting a clip needs qpos AND the working sets to be identical
+    m, tt, _ = problem("smplx", "unitree_g1")
+    clips = make_clips(m, tt, [878], T=16)               # a clip that settles with ~10 joints on their limits
+    ratio = clips.ratio(tt)
+    q_all, it_all, _, _, w_all = emu_retarget_batch_ex(m, tt, clips.pos, clips.quat, ratio)
+    qa, ita, _, _, wa = emu_retarget_batch_ex(m, tt, clips.pos[:, :9], clips.quat[:, :9], ratio)
+    qb, itb, _, _, wb = emu_retarget_batch_ex(m, tt, clips.pos[:, 9:], clips.quat[:, 9:], ratio, qpos_init=qa[:, -1], warm_state=wa)
+    np.testing.assert_allclose(np.concatenate([qa, qb], 1), q_all, atol=1e-12)
+    np.testing.assert_array_equal(np.concatenate([ita, itb], 1), it_all)
+    np.testing.assert_array_equal(wb, w_all)
+    assert w_all.any()                                               # some bound was active at the end

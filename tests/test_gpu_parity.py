@@ -267,3 +267,69 @@ def test_full_size_properties(lib, torch_cuda):
 def test_smoke_entry(lib, torch_cuda):
     import __graft_entry__ as ge
     ge.smoke()
+
+
+def test_dataset_entry_fk_epilogue_and_motion_arrays(lib, torch_cuda, tmp_path):
+    """retarget_dataset = process_file of the dataset scripts (scripts/smplx_to_robot_dataset.py:78-146) for a
+    batch: qpos as retarget_batch, local_body_pos / lowest height from the fused FK epilogue, root_pos with the
+    height adjustment and the first-frame XY re-origin, root_rot xyzw, dof_pos; ragged lengths."""
+    import pickle
+    from helpers import oracle_body_positions
+    from general_motion_retargeting_b200 import GeneralMotionRetargeting
+    m, tt, pack = problem("smplx", "booster_t1")
+    clips = make_clips(m, tt, range(5), T=20)
+    lengths = np.array([20, 13, 20, 1, 8], np.int32)
+    gmr = GeneralMotionRetargeting("smplx", "booster_t1", device=0)
+    q = gmr.retarget_batch(torch_cuda.from_numpy(clips.pos).cuda(), torch_cuda.from_numpy(clips.quat).cuda(),
+                           torch_cuda.from_numpy(clips.heights).cuda()).double().cpu().numpy()
+    motions = gmr.retarget_dataset(clips.pos, clips.quat, clips.heights, lengths=lengths, fps=30.0)
+    assert len(motions) == 5
+    for c, mo in enumerate(motions):
+        n = int(lengths[c])
+        assert mo["root_pos"].shape == (n, 3) and mo["root_rot"].shape == (n, 4) and mo["dof_pos"].shape == (n, m.nhinge)
+        assert mo["local_body_pos"].shape == (n, m.nbody, 3) and mo["link_body_list"] == m.body_names and mo["fps"] == 30.0
+        qc = q[c, :n]
+        local, world = oracle_body_positions(m, pack, qc)
+        np.testing.assert_allclose(mo["local_body_pos"], local, atol=5e-6)
+        np.testing.assert_allclose(mo["dof_pos"], qc[:, 7:], atol=1e-6)
+        np.testing.assert_allclose(mo["root_rot"], qc[:, [4, 5, 6, 3]], atol=1e-6)                # wxyz -> xyzw (:103-104)
+        ref_pos = qc[:, :3].copy()
+        ref_pos[:, 2] -= world[..., 2].min()                                                     # HEIGHT_ADJUST (:118-123)
+        ref_pos[:, :2] -= ref_pos[0, :2]                                                         # ROOT_ORIGIN_OFFSET (:125-128)
+        np.testing.assert_allclose(mo["root_pos"], ref_pos, atol=5e-6)
+    # the BVH script's switches: no height adjust, no re-origin (bvh_to_robot_dataset.py:128)
+    plain = gmr.retarget_dataset(clips.pos, clips.quat, clips.heights, lengths=lengths, height_adjust=False, root_origin_offset=False)
+    np.testing.assert_allclose(plain[1]["root_pos"], q[1, :13, :3], atol=1e-6)
+    # pkl round trip in the layout the reference's readers expect (data_loader.py:4-16)
+    paths = [str(tmp_path / f"clip{c}.pkl") for c in range(5)]
+    gmr.save_motion_pkls(motions, paths, workers=3)
+    back = pickle.load(open(paths[4], "rb"))
+    assert sorted(back) == ["dof_pos", "fps", "link_body_list", "local_body_pos", "root_pos", "root_rot"]
+    np.testing.assert_array_equal(back["dof_pos"], motions[4]["dof_pos"])
+
+
+def test_live_stream_matches_batch_and_carries_state(lib, torch_cuda):
+    """retarget(frame) per frame through gmr_stream_retarget (persistent configuration, captured CUDA graph)
+    == one retarget_batch call over the same frames; error1/error2/update_targets do not move the state."""
+    from general_motion_retargeting_b200 import GeneralMotionRetargeting
+    m, tt, _ = problem("smplx", "unitree_g1")
+    clips = make_clips(m, tt, [878, 4], T=14)              # 878 rests on joint limits: exercises the working-set carry
+    for c in range(2):
+        gmr = GeneralMotionRetargeting("smplx", "unitree_g1", actual_human_height=float(clips.heights[c]), device=0)
+        qb, itb, _ = gmr.retarget_batch(torch_cuda.from_numpy(clips.pos[c:c + 1]).cuda(), torch_cuda.from_numpy(clips.quat[c:c + 1]).cuda(),
+                                        torch_cuda.from_numpy(clips.heights[c:c + 1]).cuda(), return_info=True)
+        qb, itb = qb.cpu().numpy()[0], itb.cpu().numpy()[0]
+        for t in range(14):
+            frame = {n: (clips.pos[c, t, i], clips.quat[c, t, i]) for i, n in enumerate(tt.human_names)}
+            q = gmr.retarget(frame)
+            if t == 5:
+                e1, e2 = gmr.error1(), gmr.error2()          # NO_SOLVE calls in between must not disturb the stream
+                # error2() at the final configuration is what the stage-2 loop last evaluated; error1() is the stage-1
+                # norm at that same (post-stage-2) configuration, not the value stage 1 ended on
+                assert e2 == pytest.approx(gmr.last_errors[1], abs=1e-12) and e1 > 0
+            np.testing.assert_allclose(q, qb[t], atol=1e-12)
+            assert gmr.last_iters == tuple(itb[t])
+        # a fresh configuration starts over
+        gmr.setup_retarget_configuration()
+        frame = {n: (clips.pos[c, 0, i], clips.quat[c, 0, i]) for i, n in enumerate(tt.human_names)}
+        np.testing.assert_allclose(gmr.retarget(frame), qb[0], atol=1e-12)
