@@ -60,13 +60,41 @@ __device__ __forceinline__ void stage_consts_tma(void* dst, const void* src, uin
   }
 }
 
+// Scheduling hint for batches larger than the GPU's warp slots: clips whose first target asks for a large root
+// rotation away from the starting configuration are the ones that settle on joint limits and need several times
+// the work of a median clip (on the benchmark clips every slow clip is above 2.5 rad).  They go to
+// the front of the clip queue so that the longest chains start at t = 0 instead of in the last wave.  Pure
+// ordering: a clip's result does not depend on when or where it runs.
+//   order[0 .. n_hard) hard clips, order[C .. C + n_easy) easy clips, counts = {n_hard, n_easy}
+template <typename R, typename IO>
+__global__ void __launch_bounds__(256)
+gmr_order_kernel(const GmrConsts<R>* __restrict__ mc, const float* __restrict__ quat, const IO* __restrict__ qinit,
+                 int C, int T, int* __restrict__ counts, int* __restrict__ order) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int nhum = mc->nhum, hr = mc->hroot, nq = mc->nq;
+  const float* q = quat + ((size_t)c * T * nhum + hr) * 4;
+  const R* o = mc->hroff + 4 * hr;
+  // target root orientation = human root * table-1 rotation offset (motion_retarget.py:241-246), unnormalised
+  const float a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3];
+  const float b0 = (float)o[0], b1 = (float)o[1], b2 = (float)o[2], b3 = (float)o[3];
+  const float t0 = a0 * b0 - a1 * b1 - a2 * b2 - a3 * b3, t1 = a0 * b1 + a1 * b0 + a2 * b3 - a3 * b2,
+              t2 = a0 * b2 - a1 * b3 + a2 * b0 + a3 * b1, t3 = a0 * b3 + a1 * b2 - a2 * b1 + a3 * b0;
+  float r0, r1, r2, r3;
+  if (qinit) { const IO* qi = qinit + (size_t)c * nq + 3; r0 = (float)qi[0]; r1 = (float)qi[1]; r2 = (float)qi[2]; r3 = (float)qi[3]; }
+  else { r0 = (float)mc->qpos0[3]; r1 = (float)mc->qpos0[4]; r2 = (float)mc->qpos0[5]; r3 = (float)mc->qpos0[6]; }
+  const float dot = fabsf(t0 * r0 + t1 * r1 + t2 * r2 + t3 * r3) *
+                    rsqrtf(fmaxf((t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3) * (r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3), 1e-30f));
+  const bool hard = dot < 0.4078f;                 // rotation angle 2 acos(|dot|) > 2.3 rad
+  if (hard) order[atomicAdd(&counts[0], 1)] = c;
+  else order[C + atomicAdd(&counts[1], 1)] = c;
+}
+
 template <typename R, typename IO, int MAXWARPS>
 __global__ void __launch_bounds__(MAXWARPS * 32, 1)
 gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ GmrScal<R> ks,
-                    const GmrConsts<R>* __restrict__ gconsts, const float* __restrict__ pos, const float* __restrict__ quat,
-                    const float* __restrict__ ratio, int C, int T, const IO* __restrict__ qinit, IO* __restrict__ qout,
-                    int32_t* __restrict__ iters, IO* __restrict__ err, IO* __restrict__ tg, uint32_t flags,
-                    int* __restrict__ queue, const __grid_constant__ GmrBatchExtra ex) {
+                    const GmrConsts<R>* __restrict__ gconsts, const __grid_constant__ GmrIO<IO> io, uint32_t kflags,
+                    int* __restrict__ queue, const int* __restrict__ order) {
   extern __shared__ __align__(128) unsigned char gmr_dyn_smem[];
   unsigned char* const smem = gmr_dyn_smem;
   constexpr int CB = consts_bytes<R>();
@@ -77,30 +105,24 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
   const int wel = dm.warp_elems;
   WarpSolver<R> ws(*mc, dm, ks, (uint32_t)(16 + CB) + (uint32_t)warp * (uint32_t)wel * (uint32_t)sizeof(R), lane);
-  ws.convoy = (flags & GMR_FLAG_INTERNAL_CONVOY) != 0;
+  ws.convoy = (kflags & GMR_FLAG_INTERNAL_CONVOY) != 0;
+  const int C = io.C;
   ws.cta_active = reinterpret_cast<int*>(smem + 8);                  // second half of the mbarrier's 16-byte slot
   if (ws.convoy) {
     if (threadIdx.x == 0) *ws.cta_active = wpc;
     __syncthreads();
   }
-  const int nq = dm.nq, nhum = dm.nhum;
   // Clips come from a global queue (one atomic per clip): clips differ several-fold in the number of
   // IK steps they need, so a warp that finishes early takes the next clip instead of idling behind a
   // static assignment.  The first gridDim * wpc clips are handed out without touching the queue.
   const int nw = gridDim.x * wpc;
-  for (int c = warp * gridDim.x + blockIdx.x; c < C;) {
-    const size_t f0 = (size_t)c * T;
-    int Tc = T;                                                       // ragged batch: this clip's own length
-    if (ex.lengths) { Tc = ex.lengths[c]; Tc = Tc < 0 ? 0 : (Tc > T ? T : Tc); }
-    ws.template run_clip<IO>(pos + f0 * nhum * 3, quat + f0 * nhum * 4, ratio ? R(ratio[c]) : R(1), Tc,
-                             qinit ? qinit + (size_t)c * nq : nullptr, qout + f0 * nq,
-                             iters ? iters + 2 * f0 : nullptr, err ? err + 2 * f0 : nullptr,
-                             tg ? tg + f0 * nhum * 7 : nullptr, flags,
-                             ex.local_body_pos ? ex.local_body_pos + f0 * dm.nb * 3 : nullptr,
-                             ex.lowest_z ? ex.lowest_z + c : nullptr, ex.warm_state ? ex.warm_state + 4 * c : nullptr);
+  const int n_hard = order ? queue[1] : 0;                            // queue = {next position, n_hard, n_easy}
+  for (int p = warp * gridDim.x + blockIdx.x; p < C;) {
+    const int c = order ? (p < n_hard ? order[p] : order[C + p - n_hard]) : p;
+    ws.template run_clip<IO>(io, c);
     int nxt = 0;
     if (lane == 0) nxt = nw + atomicAdd(queue, 1);
-    c = __shfl_sync(0xffffffffu, nxt, 0);
+    p = __shfl_sync(0xffffffffu, nxt, 0);
   }
   ws.convoy_retire();
 }
@@ -221,9 +243,22 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
   static const int cv_env = getenv("GMR_CONVOY") ? atoi(getenv("GMR_CONVOY")) : 0;
   const bool convoy = cv_env != 0 && wpc >= 2;
   flags = (flags & 0xffffu) | (convoy ? GMR_FLAG_INTERNAL_CONVOY : 0u);
-  int* queue = own_queue ? own_queue : m->d_queue + (m->queue_next.fetch_add(1) % QUEUE_RING);
-  CK(cudaMemsetAsync(queue, 0, sizeof(int), st));
-  kern<<<grid, wpc * 32, smem, st>>>(sizeof(R) == 4 ? m->dims32 : m->dims64, scal_of<R>(m), dc, pos, quat, ratio, C, T, qinit, qout, iters, err, tg, flags, queue, ex);
+  int* queue = own_queue ? own_queue : m->d_queue + 4 * (m->queue_next.fetch_add(1) % QUEUE_RING);
+  CK(cudaMemsetAsync(queue, 0, 3 * sizeof(int), st));
+  // more clips than warp slots: hard clips first (stream-ordered scratch for the permutation)
+  int* order = nullptr;
+  static const int lpt_env = getenv("GMR_LPT") ? atoi(getenv("GMR_LPT")) : 1;
+  if (lpt_env && C > grid * wpc) {
+    CK(cudaMallocAsync(&order, (size_t)2 * C * sizeof(int), st));
+    gmr_order_kernel<R, IO><<<(C + 255) / 256, 256, 0, st>>>(dc, quat, qinit, C, T, queue + 1, order);
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+  }
+  GmrIO<IO> io{};
+  io.pos = pos; io.quat = quat; io.ratio = ratio; io.qinit = qinit; io.qout = qout; io.iters = iters; io.err = err; io.tg = tg;
+  io.C = C; io.T = T; io.flags = flags & 0xffffu; io.ex = ex;
+  kern<<<grid, wpc * 32, smem, st>>>(sizeof(R) == 4 ? m->dims32 : m->dims64, scal_of<R>(m), dc, io, flags, queue, order);
+  if (order) CK(cudaFreeAsync(order, st));
   g_launches.fetch_add(1);
   CK(cudaGetLastError());
   return GMR_OK;
@@ -257,7 +292,7 @@ int gmr_model_create(const GmrModelDesc* desc, int device, GmrModel** out) {
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   if (e == cudaSuccess) e = cudaMalloc(&m->d_f32, consts_bytes<float>());
   if (e == cudaSuccess) e = cudaMalloc(&m->d_f64, consts_bytes<double>());
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_queue, QUEUE_RING * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_queue, QUEUE_RING * 4 * sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(m->d_f32, 0, consts_bytes<float>());
   if (e == cudaSuccess) e = cudaMemset(m->d_f64, 0, consts_bytes<double>());
   if (e == cudaSuccess) e = cudaMemcpy(m->d_f32, &m->h_f32, sizeof(GmrConsts<float>), cudaMemcpyHostToDevice);
@@ -375,7 +410,7 @@ int stream_enqueue(GmrStream* s, uint32_t flags) {
   int rc = launch<double, double, MAXW_F64>(m, m->d_f64, (const float*)d, (const float*)(d + s->o_quat), (const float*)(d + s->o_ratio), 1, 1,
                                             (const double*)(d + s->o_state), (double*)dout, (int32_t*)(dout + s->o_it),
                                             (double*)(dout + s->o_err), (double*)(dout + s->o_tg), flags & 3u, s->st, &ex,
-                                            reinterpret_cast<int*>(d + s->o_warm + 16));
+                                            reinterpret_cast<int*>(d + s->o_warm + 16));     // {position, n_hard, n_easy}: 12 bytes
   if (rc != GMR_OK) return rc;
   if (!(flags & GMR_FLAG_NO_SOLVE))
     CK(cudaMemcpyAsync(d + s->o_state, dout, (size_t)m->h_f32.nq * 8, cudaMemcpyDeviceToDevice, s->st));

@@ -306,6 +306,14 @@ GMR_HD constexpr int gmr_schur_c(int e, int o_y) { return e < 21 ? gmr_schur_r(e
 // index of (i,j) in the packed upper triangle of a symmetric 6x6 (21 entries)
 GMR_HD constexpr int gmr_sym6(int i, int j) { return i <= j ? (i * (13 - i)) / 2 + (j - i) : (j * (13 - j)) / 2 + (i - j); }
 
+// base pointers and sizes of one batch (see include/gmr_b200.h: gmr_retarget_batch); IO = buffer type of qpos/err/targets
+template <typename IO> struct GmrIO {
+  const float* pos; const float* quat; const float* ratio;
+  const IO* qinit; IO* qout; int32_t* iters; IO* err; IO* tg;
+  int32_t C, T; uint32_t flags, _pad;
+  GmrBatchExtra ex;
+};
+
 // =============================================================================================
 template <typename R>
 struct WarpSolver {
@@ -1170,20 +1178,29 @@ struct WarpSolver {
   // exists once in the instruction stream:
   //   per stage:  curr = err(); solve; next = err(); n = 0
   //               while curr - next > tol and n < max_iter: curr = next; solve; next = err(); n += 1
+  // `io` holds the batch's base pointers (a kernel parameter: constant bank, no registers); everything
+  // clip- or frame-specific is derived from the clip index c and the frame index where it is used, so that a
+  // warp carries two integers through its clip instead of a dozen pointers.
+  // Post-solve epilogue of the dataset scripts (scripts/smplx_to_robot_dataset.py:93-123), fused: the last FK
+  // of a frame is the FK of the frame's answer, so
+  //   ex.local_body_pos [C,T,nb,3]  FK with an identity root = R_root^T (x_b - x_root), and
+  //   ex.lowest_z [C]               min over frames and bodies of the world z (the height adjustment of :118-123)
+  // cost one pass over the body poses already in shared memory.
   template <typename IO>
-  GMR_FN void run_clip(const float* pos, const float* quat, R ratio, int T, const IO* qinit, IO* qpos_out,
-                       int32_t* iters_out, IO* err_out, IO* tg_out, uint32_t flags,
-                       float* lbp_out = nullptr, float* lowest_out = nullptr, uint32_t* warm_io = nullptr) {
-    // post-solve epilogue of the dataset scripts (scripts/smplx_to_robot_dataset.py:93-123), fused: the last FK
-    // of a frame is the FK of the frame's answer, so
-    //   lbp_out [T,nb,3]  local_body_pos = FK with an identity root = R_root^T (x_b - x_root), and
-    //   lowest_out [1]    min over frames and bodies of the world z (the height adjustment of :118-123)
-    // cost one pass over the body poses already in shared memory.
-    R lowest = R(INFINITY);
-    if (qinit) set_qpos(qinit); else set_qpos(mc.qpos0);
+  GMR_FN void run_clip(const GmrIO<IO>& io, int c) {
+    const uint32_t flags = io.flags;
+    const size_t f0 = (size_t)c * io.T;
+    int T = io.T;
+    if (io.ex.lengths) { T = io.ex.lengths[c]; T = T < 0 ? 0 : (T > io.T ? io.T : T); }     // ragged batch: this clip's own length
+    const float* const pos = io.pos + f0 * dm.nhum * 3;
+    const float* const quat = io.quat + f0 * dm.nhum * 4;
+    if (io.qinit) set_qpos(io.qinit + (size_t)c * dm.nq); else set_qpos(mc.qpos0);
     warm_lo0 = warm_lo1 = warm_hi0 = warm_hi1 = 0;
-    if (warm_io) { warm_lo0 = warm_io[0]; warm_hi0 = warm_io[1]; warm_lo1 = warm_io[2]; warm_hi1 = warm_io[3]; }
+    if (io.ex.warm_state) { const uint32_t* w = io.ex.warm_state + 4 * c; warm_lo0 = w[0]; warm_hi0 = w[1]; warm_lo1 = w[2]; warm_hi1 = w[3]; }
     if (T <= 0) return;
+    GMR_LANES
+      if (lane == 0) { s_piv()[0] = io.ratio ? R(io.ratio[c]) : R(1); s_piv()[3] = R(INFINITY); }   // height ratio, running lowest z
+    GMR_END
     stage_frame(pos, quat);
     const int first_stage = dm.use1 ? 0 : 1;
     const bool any_stage = dm.use1 || dm.use2;
@@ -1195,7 +1212,7 @@ struct WarpSolver {
     for (;;) {
       if (frame_start) {
         frame_wait();
-        update_targets(ratio, (flags & GMR_FLAG_OFFSET_TO_GROUND) != 0);
+        update_targets(s_piv()[0], (flags & GMR_FLAG_OFFSET_TO_GROUND) != 0);
         if (t + 1 < T) stage_frame(pos + (size_t)(t + 1) * dm.nhum * 3, quat + (size_t)(t + 1) * dm.nhum * 4);
         stage = first_stage; nsolve = 0; n0 = n1 = 0; e0 = e1 = R(0);
         frame_start = false; need_err = true;
@@ -1228,29 +1245,30 @@ struct WarpSolver {
         continue;
       }
       if (done) {
+        const size_t f = (size_t)c * io.T + t;
         GMR_LANES
-          IO* qo = qpos_out + (size_t)t * dm.nq;
+          IO* qo = io.qout + f * dm.nq;
           for (int i = lane; i < dm.nq; i += 32) qo[i] = IO(s_q()[i]);
           if (lane == 0) {
-            if (iters_out) { iters_out[2 * t] = n0; iters_out[2 * t + 1] = n1; }
-            if (err_out) { err_out[2 * t] = IO(e0); err_out[2 * t + 1] = IO(e1); }
+            if (io.iters) { io.iters[2 * f] = n0; io.iters[2 * f + 1] = n1; }
+            if (io.err) { io.err[2 * f] = IO(e0); io.err[2 * f + 1] = IO(e1); }
           }
-          if (tg_out && lane < dm.nhum) {
-            IO* o = tg_out + ((size_t)t * dm.nhum + lane) * 7;
+          if (io.tg && lane < dm.nhum) {
+            IO* o = io.tg + (f * dm.nhum + lane) * 7;
             const R* g = s_tg() + 8 * lane;
             o[0] = IO(g[0]); o[1] = IO(g[1]); o[2] = IO(g[2]); o[3] = IO(g[4]); o[4] = IO(g[5]); o[5] = IO(g[6]); o[6] = IO(g[7]);
           }
         GMR_END
-        if (lbp_out || lowest_out) {
+        if (io.ex.local_body_pos || io.ex.lowest_z) {
           GMR_LANES
             R zmin = R(INFINITY);
             R rq[4]; g_ld4(s_rq(), rq);
             for (int b = lane; b < dm.nb; b += 32) {
               R v[4]; g_ld4(s_xp() + 4 * b, v);
               if (v[2] < zmin) zmin = v[2];
-              if (lbp_out) {
+              if (io.ex.local_body_pos) {
                 R o[3]; q_rot_inv(rq, v, o);
-                float* dst = lbp_out + ((size_t)t * dm.nb + b) * 3;
+                float* dst = io.ex.local_body_pos + (f * dm.nb + b) * 3;
                 dst[0] = (float)o[0]; dst[1] = (float)o[1]; dst[2] = (float)o[2];
               }
             }
@@ -1265,19 +1283,22 @@ struct WarpSolver {
           for (int o = 16; o > 0; o >>= 1) { const R z = __shfl_xor_sync(0xffffffffu, zm, o); if (z < zm) zm = z; }
 #endif
           zm += s_q()[2];
-          if (zm < lowest) lowest = zm;
+          const R low = s_piv()[3];
           GMR_SYNC();
+          GMR_LANES
+            if (lane == 0 && zm < low) s_piv()[3] = zm;
+          GMR_END
         }
         t++;
         if (t == T) break;
         frame_start = true;
       }
     }
-    if (lowest_out || warm_io) {
+    if (io.ex.lowest_z || io.ex.warm_state) {
       GMR_LANES
         if (lane == 0) {
-          if (lowest_out) *lowest_out = (float)lowest;
-          if (warm_io) { warm_io[0] = warm_lo0; warm_io[1] = warm_hi0; warm_io[2] = warm_lo1; warm_io[3] = warm_hi1; }
+          if (io.ex.lowest_z) io.ex.lowest_z[c] = (float)s_piv()[3];
+          if (io.ex.warm_state) { uint32_t* w = io.ex.warm_state + 4 * c; w[0] = warm_lo0; w[1] = warm_hi0; w[2] = warm_lo1; w[3] = warm_hi1; }
         }
       GMR_END
     }

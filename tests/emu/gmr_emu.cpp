@@ -23,6 +23,10 @@ static int run(const GmrModelDesc* d, const float* pos, const float* quat, const
   const int wel = dims.warp_elems;
   if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
   if (nthreads > C) nthreads = C > 0 ? C : 1;
+  GmrIO<double> io{};
+  io.pos = pos; io.quat = quat; io.ratio = ratio; io.qinit = qpos_init; io.qout = qpos_out; io.iters = iters_out; io.err = err_out;
+  io.tg = tg_out; io.C = C; io.T = T; io.flags = flags;
+  if (ex) io.ex = *ex;
   std::atomic<int> next{0};
   std::atomic<int64_t> refac{0};
   auto work = [&]() {
@@ -31,16 +35,7 @@ static int run(const GmrModelDesc* d, const float* pos, const float* quat, const
       int c = next.fetch_add(1);
       if (c >= C) break;
       auto* ws = new WarpSolver<R>(*mc, dims, ks, sm.data());
-      size_t f0 = (size_t)c * T;
-      int Tc = T;
-      if (ex && ex->lengths) { Tc = ex->lengths[c]; Tc = Tc < 0 ? 0 : (Tc > T ? T : Tc); }
-      ws->template run_clip<double>(pos + f0 * mc->nhum * 3, quat + f0 * mc->nhum * 4, ratio ? R(ratio[c]) : R(1), Tc,
-                                    qpos_init ? qpos_init + (size_t)c * mc->nq : nullptr, qpos_out + f0 * mc->nq,
-                                    iters_out ? iters_out + 2 * f0 : nullptr, err_out ? err_out + 2 * f0 : nullptr,
-                                    tg_out ? tg_out + f0 * mc->nhum * 7 : nullptr, flags,
-                                    ex && ex->local_body_pos ? ex->local_body_pos + f0 * mc->nb * 3 : nullptr,
-                                    ex && ex->lowest_z ? ex->lowest_z + c : nullptr,
-                                    ex && ex->warm_state ? ex->warm_state + 4 * c : nullptr);
+      ws->template run_clip<double>(io, c);
       refac += ws->stat_refactor;
       delete ws;
     }
