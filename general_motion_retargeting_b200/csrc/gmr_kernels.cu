@@ -90,11 +90,23 @@ gmr_order_kernel(const GmrConsts<R>* __restrict__ mc, const float* __restrict__ 
   else order[C + atomicAdd(&counts[1], 1)] = c;
 }
 
+// Second scheduling hint, for batches of one to a few waves: after frame 0 (solved for every clip by a first
+// launch) a clip that will be slow is recognisable — its task error stays above 1 where a converged clip is at
+// ~0.07.  Same list layout as above: order[0 .. n_slow) slow, order[C .. C + n_normal) the rest.
+__global__ void __launch_bounds__(256)
+gmr_classify_kernel(const double* __restrict__ state, int stride, int nq, int C, double thresh,
+                    int* __restrict__ counts, int* __restrict__ order) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (state[(size_t)c * stride + nq + 1] > thresh) order[atomicAdd(&counts[0], 1)] = c;
+  else order[C + atomicAdd(&counts[1], 1)] = c;
+}
+
 template <typename R, typename IO, int MAXWARPS>
 __global__ void __launch_bounds__(MAXWARPS * 32, 1)
 gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ GmrScal<R> ks,
                     const GmrConsts<R>* __restrict__ gconsts, const __grid_constant__ GmrIO<IO> io, uint32_t kflags,
-                    int* __restrict__ queue, const int* __restrict__ order) {
+                    int* __restrict__ queue, const int* __restrict__ order, int part_w) {
   extern __shared__ __align__(128) unsigned char gmr_dyn_smem[];
   unsigned char* const smem = gmr_dyn_smem;
   constexpr int CB = consts_bytes<R>();
@@ -116,13 +128,45 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
   // IK steps they need, so a warp that finishes early takes the next clip instead of idling behind a
   // static assignment.  The first gridDim * wpc clips are handed out without touching the queue.
   const int nw = gridDim.x * wpc;
-  const int n_hard = order ? queue[1] : 0;                            // queue = {next position, n_hard, n_easy}
-  for (int p = warp * gridDim.x + blockIdx.x; p < C;) {
-    const int c = order ? (p < n_hard ? order[p] : order[C + p - n_hard]) : p;
+  const int n_hard = order ? queue[1] : 0;                            // queue = {next position, n_hard, n_easy, next slow position}
+  // Partitioned mode (part_w > 0, slow clips known): a few SMs serve the slow list with only `pw` warps each, so
+  // that the longest sequential chains run at nearly the speed of a lone warp instead of sharing their SM's issue
+  // slots with 15-27 other clips; every other SM serves the normal list at full occupancy.  A warp whose list is
+  // empty helps with the other one.  Throughput is traded for the length of the batch's critical path.
+  const int n_norm = part_w > 0 ? queue[2] : 0;
+  bool slow_block = false, idle = false;
+  if (part_w > 0) {
+    int pw = part_w;
+    const int max_blocks = (int)gridDim.x * 2 / 5;                    // at most 40 % of the SMs
+    if (max_blocks > 0 && (n_hard + pw - 1) / pw > max_blocks) pw = (n_hard + max_blocks - 1) / max_blocks;
+    if (pw > wpc) pw = wpc;
+    const int b_slow = (n_hard + pw - 1) / pw < max_blocks ? (n_hard + pw - 1) / pw : max_blocks;
+    slow_block = (int)blockIdx.x < b_slow;
+    idle = slow_block && warp >= pw;
+  }
+  // one loop, one inlined copy of the solver: the first clip of a warp is its static slot (plain mode) or comes
+  // from the queues (partitioned mode)
+  int p = part_w > 0 ? -1 : warp * gridDim.x + blockIdx.x;
+  for (;;) {
+    int c = -1;
+    if (part_w > 0) {
+      if (idle) break;
+      if (lane == 0) {
+        if (slow_block) { const int i = atomicAdd(&queue[3], 1); if (i < n_hard) c = order[i]; }
+        if (c < 0) { const int i = atomicAdd(&queue[0], 1); if (i < n_norm) c = order[C + i]; }
+        if (c < 0 && !slow_block) { const int i = atomicAdd(&queue[3], 1); if (i < n_hard) c = order[i]; }
+      }
+      c = __shfl_sync(0xffffffffu, c, 0);
+    } else {
+      if (p < C) c = order ? (p < n_hard ? order[p] : order[C + p - n_hard]) : p;
+    }
+    if (c < 0) break;
     ws.template run_clip<IO>(io, c);
-    int nxt = 0;
-    if (lane == 0) nxt = nw + atomicAdd(queue, 1);
-    p = __shfl_sync(0xffffffffu, nxt, 0);
+    if (part_w == 0) {
+      int nxt = 0;
+      if (lane == 0) nxt = nw + atomicAdd(queue, 1);
+      p = __shfl_sync(0xffffffffu, nxt, 0);
+    }
   }
   ws.convoy_retire();
 }
@@ -243,21 +287,59 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
   static const int cv_env = getenv("GMR_CONVOY") ? atoi(getenv("GMR_CONVOY")) : 0;
   const bool convoy = cv_env != 0 && wpc >= 2;
   flags = (flags & 0xffffu) | (convoy ? GMR_FLAG_INTERNAL_CONVOY : 0u);
-  int* queue = own_queue ? own_queue : m->d_queue + 4 * (m->queue_next.fetch_add(1) % QUEUE_RING);
-  CK(cudaMemsetAsync(queue, 0, 3 * sizeof(int), st));
+  GmrIO<IO> io{};
+  io.pos = pos; io.quat = quat; io.ratio = ratio; io.qinit = qinit; io.qout = qout; io.iters = iters; io.err = err; io.tg = tg;
+  io.C = C; io.T = T; io.flags = flags & 0xffffu; io.ex = ex;
+  const GmrDims& dims = sizeof(R) == 4 ? m->dims32 : m->dims64;
+  auto next_queue = [&]() { return m->d_queue + 4 * (m->queue_next.fetch_add(1) % QUEUE_RING); };
+  const int slots = grid * wpc;
+  static const int lpt_env = getenv("GMR_LPT") ? atoi(getenv("GMR_LPT")) : 1;
+  static const int part_env = getenv("GMR_PARTITION") ? atoi(getenv("GMR_PARTITION")) : 4;   // warps per slow SM, 0 = off
+
+  // ---- batches of ~1-4 waves: frame 0 for every clip, classify, then the rest with slow clips on their own SMs ----
+  const bool two_phase = part_env > 0 && !own_queue && !convoy && !(flags & GMR_FLAG_NO_SOLVE) && T >= 16 &&
+                         C > 2 * m->num_sms * part_env && C <= 4 * m->num_sms * max_warps<R>();
+  if (two_phase) {
+    const int stride = gmr_state_stride(dims.nq);
+    char* scratch = nullptr;
+    const size_t b_state = ((size_t)C * stride * sizeof(double) + 255) & ~(size_t)255, b_order = (size_t)2 * C * sizeof(int);
+    CK(cudaMallocAsync(&scratch, b_state + 2 * b_order, st));
+    double* state = reinterpret_cast<double*>(scratch);
+    int* order1 = reinterpret_cast<int*>(scratch + b_state);
+    int* order2 = reinterpret_cast<int*>(scratch + b_state + b_order);
+    int* q1 = next_queue();
+    int* q2 = next_queue();
+    CK(cudaMemsetAsync(q1, 0, 4 * sizeof(int), st));
+    CK(cudaMemsetAsync(q2, 0, 4 * sizeof(int), st));
+    // launch A: frame 0 of every clip (balanced work: every clip starts from the same configuration)
+    GmrIO<IO> ioa = io;
+    ioa.t_begin = 0; ioa.t_end = 1; ioa.state = state;
+    kern<<<grid, wpc * 32, smem, st>>>(dims, scal_of<R>(m), dc, ioa, flags, q1, (const int*)nullptr, 0);
+    CK(cudaGetLastError());
+    gmr_classify_kernel<<<(C + 255) / 256, 256, 0, st>>>(state, stride, dims.nq, C, 1.0, q2 + 1, order2);
+    CK(cudaGetLastError());
+    // launch B: frames 1 .. T-1, partitioned
+    GmrIO<IO> iob = io;
+    iob.t_begin = 1; iob.t_end = 0; iob.state = state;
+    kern<<<grid, wpc * 32, smem, st>>>(dims, scal_of<R>(m), dc, iob, flags, q2, order2, part_env);
+    CK(cudaGetLastError());
+    CK(cudaFreeAsync(scratch, st));
+    g_launches.fetch_add(3);
+    (void)order1;
+    return GMR_OK;
+  }
+
+  int* queue = own_queue ? own_queue : next_queue();
+  CK(cudaMemsetAsync(queue, 0, 4 * sizeof(int), st));
   // more clips than warp slots: hard clips first (stream-ordered scratch for the permutation)
   int* order = nullptr;
-  static const int lpt_env = getenv("GMR_LPT") ? atoi(getenv("GMR_LPT")) : 1;
-  if (lpt_env && C > grid * wpc) {
+  if (lpt_env && C > slots) {
     CK(cudaMallocAsync(&order, (size_t)2 * C * sizeof(int), st));
     gmr_order_kernel<R, IO><<<(C + 255) / 256, 256, 0, st>>>(dc, quat, qinit, C, T, queue + 1, order);
     g_launches.fetch_add(1);
     CK(cudaGetLastError());
   }
-  GmrIO<IO> io{};
-  io.pos = pos; io.quat = quat; io.ratio = ratio; io.qinit = qinit; io.qout = qout; io.iters = iters; io.err = err; io.tg = tg;
-  io.C = C; io.T = T; io.flags = flags & 0xffffu; io.ex = ex;
-  kern<<<grid, wpc * 32, smem, st>>>(sizeof(R) == 4 ? m->dims32 : m->dims64, scal_of<R>(m), dc, io, flags, queue, order);
+  kern<<<grid, wpc * 32, smem, st>>>(dims, scal_of<R>(m), dc, io, flags, queue, order, 0);
   if (order) CK(cudaFreeAsync(order, st));
   g_launches.fetch_add(1);
   CK(cudaGetLastError());

@@ -312,7 +312,13 @@ template <typename IO> struct GmrIO {
   const IO* qinit; IO* qout; int32_t* iters; IO* err; IO* tg;
   int32_t C, T; uint32_t flags, _pad;
   GmrBatchExtra ex;
+  // a launch may cover only frames [t_begin, t_end) of every clip (t_end <= 0: to the end); `state`
+  // ([C, nq + 4] doubles: qpos | running lowest z | last error | working sets as 4 x u32) carries a clip from
+  // one launch to the next at full precision
+  int32_t t_begin, t_end;
+  double* state;
 };
+GMR_HD constexpr int gmr_state_stride(int nq) { return nq + 4; }
 
 // =============================================================================================
 template <typename R>
@@ -1194,17 +1200,28 @@ struct WarpSolver {
     if (io.ex.lengths) { T = io.ex.lengths[c]; T = T < 0 ? 0 : (T > io.T ? io.T : T); }     // ragged batch: this clip's own length
     const float* const pos = io.pos + f0 * dm.nhum * 3;
     const float* const quat = io.quat + f0 * dm.nhum * 4;
-    if (io.qinit) set_qpos(io.qinit + (size_t)c * dm.nq); else set_qpos(mc.qpos0);
+    const int tb = io.t_begin;
+    if (io.t_end > 0 && io.t_end < T) T = io.t_end;
+    if (tb >= T) return;                                              // nothing of this clip in this launch's frame range
+    const bool resume = tb > 0 && io.state;
+    {
+    const double* const st = io.state ? io.state + (size_t)c * gmr_state_stride(dm.nq) : nullptr;   // not kept live: re-derived at the end
+    if (resume) set_qpos(st);
+    else if (io.qinit) set_qpos(io.qinit + (size_t)c * dm.nq);
+    else set_qpos(mc.qpos0);
     warm_lo0 = warm_lo1 = warm_hi0 = warm_hi1 = 0;
-    if (io.ex.warm_state) { const uint32_t* w = io.ex.warm_state + 4 * c; warm_lo0 = w[0]; warm_hi0 = w[1]; warm_lo1 = w[2]; warm_hi1 = w[3]; }
-    if (T <= 0) return;
+    {
+      const uint32_t* w = resume ? reinterpret_cast<const uint32_t*>(st + dm.nq + 2) : (io.ex.warm_state ? io.ex.warm_state + 4 * c : nullptr);
+      if (w) { warm_lo0 = w[0]; warm_hi0 = w[1]; warm_lo1 = w[2]; warm_hi1 = w[3]; }
+    }
     GMR_LANES
-      if (lane == 0) { s_piv()[0] = io.ratio ? R(io.ratio[c]) : R(1); s_piv()[3] = R(INFINITY); }   // height ratio, running lowest z
+      if (lane == 0) { s_piv()[0] = io.ratio ? R(io.ratio[c]) : R(1); s_piv()[3] = resume ? R(st[dm.nq]) : R(INFINITY); }   // height ratio, running lowest z
     GMR_END
-    stage_frame(pos, quat);
+    }
+    stage_frame(pos + (size_t)tb * dm.nhum * 3, quat + (size_t)tb * dm.nhum * 4);
     const int first_stage = dm.use1 ? 0 : 1;
     const bool any_stage = dm.use1 || dm.use2;
-    int t = 0, stage = first_stage, nsolve = 0;
+    int t = tb, stage = first_stage, nsolve = 0;
     int n0 = 0, n1 = 0;
     R e0 = R(0), e1 = R(0);
     R curr = R(0);
@@ -1293,6 +1310,18 @@ struct WarpSolver {
         if (t == T) break;
         frame_start = true;
       }
+    }
+    if (io.state) {                                                   // hand-over to the launch that continues this clip
+      double* const st = io.state + (size_t)c * gmr_state_stride(dm.nq);
+      GMR_LANES
+        for (int i = lane; i < dm.nq; i += 32) st[i] = (double)s_q()[i];
+        if (lane == 0) {
+          st[dm.nq] = (double)s_piv()[3];
+          st[dm.nq + 1] = (double)(dm.use2 ? e1 : e0);
+          uint32_t* w = reinterpret_cast<uint32_t*>(st + dm.nq + 2);
+          w[0] = warm_lo0; w[1] = warm_hi0; w[2] = warm_lo1; w[3] = warm_hi1;
+        }
+      GMR_END
     }
     if (io.ex.lowest_z || io.ex.warm_state) {
       GMR_LANES

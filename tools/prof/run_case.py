@@ -13,7 +13,8 @@ same = len(sys.argv) > 4 and sys.argv[4] == "same"
 robot, cfg, _ = params.load_pack("smplx", "unitree_g1")
 table = compile_task_table(robot, cfg)
 gmr = GeneralMotionRetargeting("smplx", "unitree_g1", device=0)
-clips = make_clips(robot, table, range(1 if same else C), T=T, device="cuda")   # same draws as on the CPU, seconds instead of a minute
+first = int(os.environ.get("CASE_CLIP", "0"))
+clips = make_clips(robot, table, range(first, first + (1 if same else C)), T=T, device="cuda")   # same draws as on the CPU, seconds instead of a minute
 rep = (lambda x: np.repeat(x[:1], C, axis=0)) if same else (lambda x: x)
 dp, dq, dh = (torch.from_numpy(np.ascontiguousarray(rep(x))).cuda() for x in (clips.pos, clips.quat, clips.heights))
 for _ in range(3):
