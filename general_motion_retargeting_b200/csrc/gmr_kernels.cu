@@ -146,7 +146,7 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
   }
   // one loop, one inlined copy of the solver: the first clip of a warp is its static slot (plain mode) or comes
   // from the queues (partitioned mode)
-  int p = part_w > 0 ? -1 : warp * gridDim.x + blockIdx.x;
+  int p = part_w > 0 ? -1 : warp * (int)gridDim.x + (int)blockIdx.x;
   for (;;) {
     int c = -1;
     if (part_w > 0) {

@@ -811,9 +811,10 @@ struct WarpSolver {
 
   // one depth of the elimination: the hinges of depth lv publish their rows, their ancestors absorb them
   template <int NCH>
-  GMR_FN void eliminate_depth(int lv) {
+  GMR_FN void eliminate_depth(int lv, uint32_t pinned) {
+    // a pinned hinge's row is the identity (apply_pins): eliminating it changes nothing, so it is skipped
     GMR_LANES
-      if (GMR_DEPTH == lv) {
+      if (GMR_DEPTH == lv && !((pinned >> lane) & 1u)) {
         const R di = g_rcp_pos(L.dg);
         L.dinv = di;
         R* o = s_L() + dm.rs * lane;
@@ -821,7 +822,7 @@ struct WarpSolver {
         g_st4(o + dm.o_y, L.rhs, di, R(0), R(0));
       }
     GMR_END
-    uint32_t rem = mc.lvl_mask[lv];
+    uint32_t rem = mc.lvl_mask[lv] & ~pinned;
     while (rem) {
       const int k = GMR_CTZ(rem);
       rem &= rem - 1u;
@@ -857,7 +858,8 @@ struct WarpSolver {
   // their 6x6 Schur complement is accumulated afterwards by 27 lanes (21 entries + 6 right-hand sides) from
   // the published rows and solved densely; the back substitution walks the depths root -> leaves.
   // For G1: 10 depths instead of 29 sequential pivots, rows of <= 16 slots instead of 35.
-  GMR_FN void factor_solve(bool pinned_any) {
+  GMR_FN void factor_solve(uint32_t pinned) {
+    const bool pinned_any = pinned != 0;
     // per-lane constants of this factorisation: my descendants, my entry (r, cc) of the base block
     // (lanes 0..20: packed upper triangle; lanes 21..26: the right-hand side, "column" o_y)
     GMR_LANES
@@ -867,9 +869,9 @@ struct WarpSolver {
       // slots [0, 5 + lv) = base + strict ancestors; the chunk count is a template argument so that shallow
       // depths do not issue (predicated-off) work for slots they do not have
       switch ((5 + lv + 3) >> 2) {
-        case 2: eliminate_depth<2>(lv); break;
-        case 3: eliminate_depth<3>(lv); break;
-        default: eliminate_depth<GMR_NS / 4>(lv); break;
+        case 2: eliminate_depth<2>(lv, pinned); break;
+        case 3: eliminate_depth<3>(lv, pinned); break;
+        default: eliminate_depth<GMR_NS / 4>(lv, pinned); break;
       }
     }
     GMR_LANES
@@ -984,7 +986,7 @@ struct WarpSolver {
       build_rows();
       if (!check) {
         if (pinned) apply_pins(pinned);
-        factor_solve(pinned != 0);
+        factor_solve(pinned);
         stat_refactor++;
         // ratio test towards the candidate
         bool blocked = false;
@@ -1010,7 +1012,18 @@ struct WarpSolver {
         GMR_END
         if (blocked) {
           R alpha = R(1); int blk = -1;
+#ifdef GMR_EMULATE
           for (int j = 0; j < dm.nh; j++) { const R a = s_red()[j]; if (a < alpha) { alpha = a; blk = j; } }
+#else
+          {   // smallest step and the lowest hinge that attains it: butterfly min + ballot
+            const R mine = lane_ < dm.nh ? s_red()[lane_] : R(INFINITY);
+            R mn = mine;
+            GMR_UNROLL
+            for (int o = 16; o > 0; o >>= 1) { const R v = __shfl_xor_sync(0xffffffffu, mn, o); if (v < mn) mn = v; }
+            alpha = mn;
+            blk = __ffs(__ballot_sync(0xffffffffu, mine == mn)) - 1;
+          }
+#endif
           GMR_SYNC();
           if (alpha < R(0)) alpha = R(0);
           GMR_LANES
@@ -1060,19 +1073,38 @@ struct WarpSolver {
           s_red()[lane] = lam;
         }
       GMR_END
+      // release: the first two checks of a solve drop EVERY bound with a multiplier of the wrong sign (a
+      // stage switch typically flips several at once), later ones only the worst (the textbook rule, which
+      // cannot cycle).  Whatever the path, the loop only ends on a point that passes this KKT check.
       R lmin = R(0), gmax = R(1); int worst = -1;
+      uint32_t drop_all = 0;
+#ifdef GMR_EMULATE
       for (int j = 0; j < dm.nh; j++) if ((pinned >> j) & 1u) {
         const R l = s_red()[j];
         if (g_abs(l) > gmax) gmax = g_abs(l);
         if (worst < 0 || l < lmin) { lmin = l; worst = j; }
       }
+      for (int j = 0; j < dm.nh; j++) if (((pinned >> j) & 1u) && s_red()[j] < -GmrEps<R>::lam * gmax) drop_all |= 1u << j;
+#else
+      {   // butterfly max |lambda| and min lambda over the pinned lanes, ballots for the argmin and the drop set
+        const bool mine_pinned = (pinned >> lane_) & 1u;
+        const R l = mine_pinned ? s_red()[lane_] : R(INFINITY);
+        R mx = mine_pinned ? g_abs(l) : R(0), mn = l;
+        GMR_UNROLL
+        for (int o = 16; o > 0; o >>= 1) {
+          const R a = __shfl_xor_sync(0xffffffffu, mx, o), b = __shfl_xor_sync(0xffffffffu, mn, o);
+          if (a > mx) mx = a;
+          if (b < mn) mn = b;
+        }
+        if (mx > gmax) gmax = mx;
+        lmin = mn;
+        worst = __ffs(__ballot_sync(0xffffffffu, mine_pinned && l == mn)) - 1;
+        drop_all = __ballot_sync(0xffffffffu, mine_pinned && l < -GmrEps<R>::lam * gmax);
+      }
+#endif
       if (worst < 0 || lmin >= -GmrEps<R>::lam * gmax) { GMR_SYNC(); break; }
-      // release: the first two checks of a solve drop EVERY bound with a multiplier of the wrong sign (a
-      // stage switch typically flips several at once), later ones only the worst (the textbook rule, which
-      // cannot cycle).  Whatever the path, the loop only ends on a point that passes this KKT check.
       uint32_t drop = 1u << worst;
-      if (nchecks < 2)
-        for (int j = 0; j < dm.nh; j++) if (((pinned >> j) & 1u) && s_red()[j] < -GmrEps<R>::lam * gmax) drop |= 1u << j;
+      if (nchecks < 2) drop |= drop_all;
       nchecks++;
       GMR_SYNC();
       pin_lo &= ~drop; pin_hi &= ~drop;
