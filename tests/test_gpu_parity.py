@@ -333,3 +333,30 @@ def test_live_stream_matches_batch_and_carries_state(lib, torch_cuda):
         gmr.setup_retarget_configuration()
         frame = {n: (clips.pos[c, 0, i], clips.quat[c, 0, i]) for i, n in enumerate(tt.human_names)}
         np.testing.assert_allclose(gmr.retarget(frame), qb[0], atol=1e-12)
+
+
+def test_two_phase_schedule_is_invisible(lib, torch_cuda):
+    """Batches of 1-4 GPU waves run as frame 0 -> classify -> frames 1.. with slow clips on their own SMs
+    (DESIGN.md §3), carried across the launches by a float64 state.  Pure scheduling: every output, including the
+    ragged lengths and the fused FK epilogue (running lowest height), must be bit-identical to a small batch that
+    takes the plain single-launch path."""
+    torch = torch_cuda
+    from general_motion_retargeting_b200 import GeneralMotionRetargeting
+    m, tt, _ = problem("smplx", "unitree_g1")
+    Cn, T = 1400, 18                                           # > 2 * 148 SMs * 4 warps: two-phase
+    clips = make_clips(m, tt, range(800, 800 + Cn), T=T, device="cuda")
+    rng = np.random.default_rng(5)
+    lengths = rng.integers(1, T + 1, Cn).astype(np.int32)
+    lengths[:4] = [T, 1, 2, T]
+    g = GeneralMotionRetargeting("smplx", "unitree_g1")
+    big = g.retarget_dataset(clips.pos, clips.quat, clips.heights, lengths=lengths, as_numpy=False)
+    sel = np.r_[0:40, 700:730, Cn - 30:Cn]                     # 100 clips: plain path
+    small = g.retarget_dataset(clips.pos[sel], clips.quat[sel], clips.heights[sel], lengths=lengths[sel], as_numpy=False)
+    idx = torch.from_numpy(sel).cuda()
+    for k in ("qpos", "root_pos", "root_rot", "dof_pos", "local_body_pos", "lowest_z"):
+        assert torch.equal(big[k][idx], small[k]), k
+    # and the iteration counts / errors through the batch entry
+    pos, quat, h = torch.from_numpy(clips.pos).cuda(), torch.from_numpy(clips.quat).cuda(), torch.from_numpy(clips.heights).cuda()
+    q, it, err = g.retarget_batch(pos, quat, h, return_info=True)
+    qs, its, errs = g.retarget_batch(pos[idx], quat[idx], h[idx], return_info=True)
+    assert torch.equal(q[idx], qs) and torch.equal(it[idx], its) and torch.equal(err[idx], errs)
