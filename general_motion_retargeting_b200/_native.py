@@ -142,6 +142,11 @@ def load_library() -> C.CDLL:
     lib.gmr_stream_reset.restype = C.c_int
     lib.gmr_stream_retarget.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, vp, vp]
     lib.gmr_stream_retarget.restype = C.c_int
+    lib.gmr_produce_bvh_frames.argtypes = [f32p, f32p, i32p, C.c_int32, C.c_int32, i32p, i32p, C.c_int32, f32p, f32p, vp]
+    lib.gmr_produce_bvh_frames.restype = C.c_int
+    lib.gmr_produce_smplx_frames.argtypes = [f32p, f32p, f32p, i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, i32p, C.c_int32,
+                                             f32p, f32p, vp]
+    lib.gmr_produce_smplx_frames.restype = C.c_int
     lib.gmr_launch_count.argtypes = []
     lib.gmr_launch_count.restype = C.c_int64
     lib.gmr_last_error.argtypes = []
@@ -157,4 +162,5 @@ EXPORTED_SYMBOLS = [
     "gmr_retarget_batch_host", "gmr_launch_count", "gmr_last_error", "gmr_kernel_info",
     "gmr_retarget_batch_ex", "gmr_finalize_motion",
     "gmr_stream_create", "gmr_stream_destroy", "gmr_stream_reset", "gmr_stream_retarget",
+    "gmr_produce_bvh_frames", "gmr_produce_smplx_frames",
 ]

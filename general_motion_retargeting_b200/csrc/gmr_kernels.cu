@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "gmr_solver.cuh"
+#include "gmr_producers.cuh"
 
 #define GMR_FLAG_INTERNAL_CONVOY 0x80000000u   // set by launch(), never by callers
 
@@ -685,6 +686,60 @@ int gmr_retarget_batch_host(GmrModel* m, const float* pos, const float* quat, co
     if (e != cudaSuccess && rc == GMR_OK) rc = cuda_err(e, "cudaStreamSynchronize");
   }
   return rc;
+}
+
+// ---- human-frame producers -------------------------------------------------------------------------------
+static int producer_grid(int frames) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = (frames + 7) / 8, cap = sms * 8;          // 8 frames per block, a multiple of the SM count
+  return blocks < cap ? (blocks < 1 ? 1 : blocks) : cap;
+}
+
+int gmr_produce_bvh_frames(const float* lrot, const float* lpos, const int32_t* parents, int32_t F, int32_t J,
+                           const int32_t* pos_joint, const int32_t* rot_joint, int32_t nh,
+                           float* pos_out, float* quat_out, void* cuda_stream) {
+  if (F < 0) return set_err(GMR_EINVAL, "negative frame count");
+  if (F == 0) return GMR_OK;
+  if (!lrot || !lpos || !parents || !pos_joint || !rot_joint || !pos_out || !quat_out) return set_err(GMR_EINVAL, "null argument");
+  if ((reinterpret_cast<uintptr_t>(lrot) & 15u) || (reinterpret_cast<uintptr_t>(quat_out) & 15u)) return set_err(GMR_EINVAL, "quaternion arrays must be 16-byte aligned");
+  // positions and orientations may come from different joints (FootMod): both sets of chains are needed
+  std::vector<int32_t> both(2 * (size_t)(nh > 0 ? nh : 0));
+  for (int b = 0; b < nh; b++) { both[b] = rot_joint[b]; both[nh + b] = pos_joint[b]; }
+  GmrChain ch{};
+  const char* why = "";
+  if (nh < 1 || nh > 16) return set_err(GMR_ELIMIT, "1..16 output bodies");
+  int rc = gmr_prod::build_chain(parents, J, both.data(), 2 * nh, &ch, &why);
+  if (rc != 0) return set_err(rc == -4 ? GMR_ELIMIT : GMR_EINVAL, why);
+  for (int b = 0; b < nh; b++) ch.pos_lane[b] = ch.rot_lane[nh + b];
+  ch.nh = nh;
+  gmr_prod::gmr_bvh_kernel<<<producer_grid(F), 256, 0, (cudaStream_t)cuda_stream>>>(ch, lrot, lpos, F, J, pos_out, quat_out);
+  g_launches.fetch_add(1);
+  CK(cudaGetLastError());
+  return GMR_OK;
+}
+
+int gmr_produce_smplx_frames(const float* global_orient, const float* full_pose, const float* joints, const int32_t* parents,
+                             int32_t F, int32_t NJ, int32_t NJ_joints, int32_t F_out, const int32_t* body_joint, int32_t nh,
+                             float* pos_out, float* quat_out, void* cuda_stream) {
+  if (F < 0 || F_out < 0) return set_err(GMR_EINVAL, "negative frame count");
+  if (F == 0 || F_out == 0) return GMR_OK;
+  if (!global_orient || !full_pose || !joints || !parents || !body_joint || !pos_out || !quat_out) return set_err(GMR_EINVAL, "null argument");
+  if (reinterpret_cast<uintptr_t>(quat_out) & 15u) return set_err(GMR_EINVAL, "quat_out must be 16-byte aligned");
+  if (F_out > F) return set_err(GMR_EINVAL, "F_out must not exceed F (the reference only resamples downwards)");
+  GmrChain ch{};
+  const char* why = "";
+  int rc = gmr_prod::build_chain(parents, NJ, body_joint, nh, &ch, &why);
+  if (rc != 0) return set_err(rc == -4 ? GMR_ELIMIT : GMR_EINVAL, why);
+  for (int b = 0; b < nh; b++) {
+    if (body_joint[b] >= NJ_joints) return set_err(GMR_EINVAL, "joint index beyond the joints array");
+    ch.pos_lane[b] = (uint8_t)body_joint[b];
+  }
+  gmr_prod::gmr_smplx_kernel<<<producer_grid(F_out), 256, 0, (cudaStream_t)cuda_stream>>>(
+      ch, global_orient, full_pose, joints, F, NJ, NJ_joints, F_out, F_out != F ? 1 : 0, pos_out, quat_out);
+  g_launches.fetch_add(1);
+  CK(cudaGetLastError());
+  return GMR_OK;
 }
 
 int64_t gmr_launch_count(void) { return g_launches.load(); }

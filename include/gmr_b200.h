@@ -148,6 +148,25 @@ int gmr_stream_reset(GmrStream* stream, const double* qpos);
 int gmr_stream_retarget(GmrStream* stream, const float* pos, const float* quat, uint32_t flags,
                         double* qpos_out, int32_t* iters_out, double* err_out, double* targets_out);
 
+/* ---- human-frame producers: the loaders' arithmetic after file parsing, for a batch of frames ---------------
+ * Output = the solver's input layout (pos [F,nh,3] metres Z-up, quat [F,nh,4] wxyz), device pointers; the small
+ * index arrays (parents, *_joint) are HOST pointers.  Frames of many clips can be concatenated (frames are
+ * independent) except across a resampling call.
+ *
+ * BVH / LAFAN1 (replaces utils/lafan1.py:17-35 after read_bvh: quat_fk of lafan_vendor/utils.py:88-103, the
+ * Y-up -> Z-up rotation, cm -> m, and the LeftFootMod / RightFootMod bodies):
+ *   lrot [F,J,4] local quaternions wxyz, lpos [F,J,3] local positions in cm (Anim.quats / Anim.pos),
+ *   body b takes its position from joint pos_joint[b] and its orientation from joint rot_joint[b]. */
+int gmr_produce_bvh_frames(const float* lrot, const float* lpos, const int32_t* parents, int32_t F, int32_t J,
+                           const int32_t* pos_joint, const int32_t* rot_joint, int32_t nh,
+                           float* pos_out, float* quat_out, void* cuda_stream);
+/* SMPL-X (replaces utils/smpl.py:127-196 after the body model's forward pass): global_orient [F,3] and
+ * full_pose [F,NJ,3] axis-angle, joints [F,NJ_joints,3]; F_out < F resamples like the reference
+ * (target times linspace(0, F-1, F_out), SLERP of neighbouring rotations, linear positions), F_out == F copies. */
+int gmr_produce_smplx_frames(const float* global_orient, const float* full_pose, const float* joints, const int32_t* parents,
+                             int32_t F, int32_t NJ, int32_t NJ_joints, int32_t F_out, const int32_t* body_joint, int32_t nh,
+                             float* pos_out, float* quat_out, void* cuda_stream);
+
 /* float64 variant of the same kernel (identical semantics; qpos_init/qpos_out/err_out/
  * targets_out are double).  Exists so that parity can be checked without float32 rounding. */
 int gmr_retarget_batch_f64(GmrModel* model, const float* pos, const float* quat, const float* ratio,
