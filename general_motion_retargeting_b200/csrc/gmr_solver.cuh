@@ -822,26 +822,58 @@ struct WarpSolver {
         g_st4(o + dm.o_y, L.rhs, di, R(0), R(0));
       }
     GMR_END
+    // float32: two pivots per pass, branch-free — every lane loads both published rows (broadcast reads) and absorbs
+    // them with a multiplier that is zero unless the lane is an ancestor of that pivot; a lone pivot is paired with
+    // itself at zero weight.  No divergent branch, the loads of the second pivot overlap the FMAs of the first
+    // (lone warp -8 %).  float64 keeps one pivot per pass behind a branch: its FMAs are the scarce resource (the FP64
+    // pipe is half rate), and the paired form issues ~10 % more of them.
     uint32_t rem = mc.lvl_mask[lv] & ~pinned;
-    while (rem) {
-      const int k = GMR_CTZ(rem);
-      rem &= rem - 1u;
-      GMR_LANES
-        const R* pk = s_L() + dm.rs * k;
-        const R yk = pk[dm.o_y], dk = pk[dm.o_y + 1];
-        if ((GMR_DESC >> k) & 1u) {
-          const R hki = pk[5 + GMR_DEPTH];
-          const R a = hki * dk;
-          GMR_UNROLL
-          for (int c = 0; c < NCH; c++) {
-            R v[4]; g_ld4(pk + 4 * c, v);
-            L.row[4 * c] -= a * v[0]; L.row[4 * c + 1] -= a * v[1]; L.row[4 * c + 2] -= a * v[2]; L.row[4 * c + 3] -= a * v[3];
+    if (sizeof(R) == 8) {
+      while (rem) {
+        const int k = GMR_CTZ(rem);
+        rem &= rem - 1u;
+        GMR_LANES
+          const R* pk = s_L() + dm.rs * k;
+          const R yk = pk[dm.o_y], dk = pk[dm.o_y + 1];
+          if ((GMR_DESC >> k) & 1u) {
+            const R hki = pk[5 + GMR_DEPTH];
+            const R a = hki * dk;
+            GMR_UNROLL
+            for (int c = 0; c < NCH; c++) {
+              R v[4]; g_ld4(pk + 4 * c, v);
+              L.row[4 * c] -= a * v[0]; L.row[4 * c + 1] -= a * v[1]; L.row[4 * c + 2] -= a * v[2]; L.row[4 * c + 3] -= a * v[3];
+            }
+            L.dg -= a * hki;
+            L.rhs -= a * yk;
           }
-          L.dg -= a * hki;
-          L.rhs -= a * yk;
+          // base block: S = A_bb - sum_k (1/d_k) h_k h_k^T,  b = b_b - sum_k (1/d_k) h_k y_k,  h_k = base slots of row k
+          if (lane < 27) L.sacc += pk[GMR_SR] * dk * pk[GMR_SC];
+        GMR_END_NOSYNC
+      }
+      return;
+    }
+    while (rem) {
+      const int k0 = GMR_CTZ(rem);
+      rem &= rem - 1u;
+      const bool two = rem != 0;
+      const int k1 = two ? GMR_CTZ(rem) : k0;
+      rem &= rem - 1u;                                               // (0 & anything) stays 0
+      GMR_LANES
+        const R* p0 = s_L() + dm.rs * k0;
+        const R* p1 = s_L() + dm.rs * k1;
+        const R y0 = p0[dm.o_y], d0 = p0[dm.o_y + 1], y1 = p1[dm.o_y], d1 = two ? p1[dm.o_y + 1] : R(0);
+        const R h0 = p0[5 + GMR_DEPTH], h1 = p1[5 + GMR_DEPTH];
+        const R a0 = ((GMR_DESC >> k0) & 1u) ? h0 * d0 : R(0), a1 = ((GMR_DESC >> k1) & 1u) ? h1 * d1 : R(0);
+        GMR_UNROLL
+        for (int c = 0; c < NCH; c++) {
+          R v[4], w[4]; g_ld4(p0 + 4 * c, v); g_ld4(p1 + 4 * c, w);
+          L.row[4 * c] -= a0 * v[0]; L.row[4 * c + 1] -= a0 * v[1]; L.row[4 * c + 2] -= a0 * v[2]; L.row[4 * c + 3] -= a0 * v[3];
+          L.row[4 * c] -= a1 * w[0]; L.row[4 * c + 1] -= a1 * w[1]; L.row[4 * c + 2] -= a1 * w[2]; L.row[4 * c + 3] -= a1 * w[3];
         }
+        L.dg -= a0 * h0; L.dg -= a1 * h1;
+        L.rhs -= a0 * y0; L.rhs -= a1 * y1;
         // base block: S = A_bb - sum_k (1/d_k) h_k h_k^T,  b = b_b - sum_k (1/d_k) h_k y_k,  h_k = base slots of row k
-        if (lane < 27) L.sacc += pk[GMR_SR] * dk * pk[GMR_SC];
+        if (lane < 27) { L.sacc += p0[GMR_SR] * d0 * p0[GMR_SC]; L.sacc += p1[GMR_SR] * d1 * p1[GMR_SC]; }
       GMR_END_NOSYNC
     }
   }
