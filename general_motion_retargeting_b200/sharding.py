@@ -20,6 +20,17 @@ def all_shards(num_clips: int, world: int) -> List[Tuple[int, int]]:
     return [clip_shard(num_clips, r, world) for r in range(world)]
 
 
+def bucket_by_robot(robot_of_clip) -> dict:
+    """Mixed-robot batches (BASELINE.json configs[4]: clip i -> robot i mod 5): a launch is robot-uniform (one
+    constant block per CTA), so the host groups the clip indices by robot; each bucket is retargeted by its own
+    `GeneralMotionRetargeting(src, robot)` and the results are scattered back by index.  Returns
+    {robot: ascending list of clip indices}."""
+    out: dict = {}
+    for i, r in enumerate(robot_of_clip):
+        out.setdefault(r, []).append(i)
+    return out
+
+
 def max_over_ranks(value: float) -> float:
     """Max of a host scalar over the default process group (no-op without one)."""
     import torch

@@ -23,6 +23,14 @@ def test_shards_partition_the_clips():
         clip_shard(10, 2, 2)
 
 
+def test_bucket_by_robot_groups_and_preserves_order():
+    from general_motion_retargeting_b200.sharding import bucket_by_robot
+    robots = ["g1", "t1", "toddy", "n1", "pm01"]
+    b = bucket_by_robot([robots[i % 5] for i in range(23)])
+    assert sorted(b) == sorted(robots) and sum(len(v) for v in b.values()) == 23
+    assert b["g1"] == [0, 5, 10, 15, 20] and b["pm01"] == [4, 9, 14, 19]
+
+
 WORKER = r'''
 import os, sys
 sys.path.insert(0, os.environ["GMR_ROOT"]); sys.path.insert(0, os.path.join(os.environ["GMR_ROOT"], "tests"))
