@@ -236,6 +236,16 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// stream-ordered scratch memory (cudaMallocAsync) released in stream order when the scope ends
+struct StreamScratch {
+  cudaStream_t st; char* p = nullptr;
+  explicit StreamScratch(cudaStream_t s) : st(s) {}
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(reinterpret_cast<void**>(&p), bytes, st); }
+  ~StreamScratch() { if (p) { cudaFreeAsync(p, st); } }
+  StreamScratch(const StreamScratch&) = delete;
+  StreamScratch& operator=(const StreamScratch&) = delete;
+};
+
 template <typename R> int max_warps();
 template <> int max_warps<float>() { return MAXW_F32; }
 template <> int max_warps<double>() { return MAXW_F64; }
@@ -275,10 +285,12 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
   const int wpc = pick_wpc<R>(m, C);
   const size_t smem = smem_bytes<R>(m, wpc);
   if (smem > (size_t)m->max_smem) return set_err(GMR_ELIMIT, "model does not fit in shared memory");
-  static thread_local const void* configured = nullptr;   // opt in to the large dynamic allocation once per kernel
-  if (configured != (const void*)kern) {
+  // opt in to the large dynamic allocation: once per (kernel instantiation, device) — the attribute is per device
+  static std::atomic<uint64_t> configured{0};
+  const uint64_t dev_bit = 1ull << (m->device & 63);
+  if (!(configured.load(std::memory_order_acquire) & dev_bit)) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m->max_smem));
-    configured = (const void*)kern;
+    configured.fetch_or(dev_bit, std::memory_order_release);
   }
   int grid = (C + wpc - 1) / wpc;
   if (grid > m->num_sms * ctas_per_sm()) grid = m->num_sms * ctas_per_sm();
@@ -302,12 +314,11 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
                          C > 2 * m->num_sms * part_env && C <= 4 * m->num_sms * max_warps<R>();
   if (two_phase) {
     const int stride = gmr_state_stride(dims.nq);
-    char* scratch = nullptr;
     const size_t b_state = ((size_t)C * stride * sizeof(double) + 255) & ~(size_t)255, b_order = (size_t)2 * C * sizeof(int);
-    CK(cudaMallocAsync(&scratch, b_state + 2 * b_order, st));
-    double* state = reinterpret_cast<double*>(scratch);
-    int* order1 = reinterpret_cast<int*>(scratch + b_state);
-    int* order2 = reinterpret_cast<int*>(scratch + b_state + b_order);
+    StreamScratch scratch(st);                               // freed in stream order on every exit path
+    CK(scratch.alloc(b_state + b_order));
+    double* state = reinterpret_cast<double*>(scratch.p);
+    int* order2 = reinterpret_cast<int*>(scratch.p + b_state);
     int* q1 = next_queue();
     int* q2 = next_queue();
     CK(cudaMemsetAsync(q1, 0, 4 * sizeof(int), st));
@@ -327,9 +338,7 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
     static const int pct_env = getenv("GMR_PARTITION_PCT") ? atoi(getenv("GMR_PARTITION_PCT")) : 55;
     kern<<<grid, wpc * 32, smem, st>>>(dims, scal_of<R>(m), dc, iob, flags, q2, order2, part_env, pct_env);
     CK(cudaGetLastError());
-    CK(cudaFreeAsync(scratch, st));
     g_launches.fetch_add(3);
-    (void)order1;
     return GMR_OK;
   }
 
@@ -337,14 +346,15 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
   CK(cudaMemsetAsync(queue, 0, 4 * sizeof(int), st));
   // more clips than warp slots: hard clips first (stream-ordered scratch for the permutation)
   int* order = nullptr;
+  StreamScratch scratch(st);
   if (lpt_env && C > slots) {
-    CK(cudaMallocAsync(&order, (size_t)2 * C * sizeof(int), st));
+    CK(scratch.alloc((size_t)2 * C * sizeof(int)));
+    order = reinterpret_cast<int*>(scratch.p);
     gmr_order_kernel<R, IO><<<(C + 255) / 256, 256, 0, st>>>(dc, quat, qinit, C, T, queue + 1, order);
     g_launches.fetch_add(1);
     CK(cudaGetLastError());
   }
   kern<<<grid, wpc * 32, smem, st>>>(dims, scal_of<R>(m), dc, io, flags, queue, order, 0, 0);
-  if (order) CK(cudaFreeAsync(order, st));
   g_launches.fetch_add(1);
   CK(cudaGetLastError());
   return GMR_OK;

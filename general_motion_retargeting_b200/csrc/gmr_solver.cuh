@@ -828,7 +828,7 @@ struct WarpSolver {
     // (lone warp -8 %).  float64 keeps one pivot per pass behind a branch: its FMAs are the scarce resource (the FP64
     // pipe is half rate), and the paired form issues ~10 % more of them.
     uint32_t rem = mc.lvl_mask[lv] & ~pinned;
-    if (sizeof(R) == 8) {
+    if constexpr (sizeof(R) == 8) {
       while (rem) {
         const int k = GMR_CTZ(rem);
         rem &= rem - 1u;
@@ -850,8 +850,7 @@ struct WarpSolver {
           if (lane < 27) L.sacc += pk[GMR_SR] * dk * pk[GMR_SC];
         GMR_END_NOSYNC
       }
-      return;
-    }
+    } else {
     while (rem) {
       const int k0 = GMR_CTZ(rem);
       rem &= rem - 1u;
@@ -875,6 +874,7 @@ struct WarpSolver {
         // base block: S = A_bb - sum_k (1/d_k) h_k h_k^T,  b = b_b - sum_k (1/d_k) h_k y_k,  h_k = base slots of row k
         if (lane < 27) { L.sacc += p0[GMR_SR] * d0 * p0[GMR_SC]; L.sacc += p1[GMR_SR] * d1 * p1[GMR_SC]; }
       GMR_END_NOSYNC
+    }
     }
   }
 
