@@ -140,3 +140,42 @@ def test_fk_epilogue_ragged_lengths_and_warm_state(built):
     np.testing.assert_array_equal(np.concatenate([ita, itb], 1), it_all)
     np.testing.assert_array_equal(wb, w_all)
     assert w_all.any()                                               # some bound was active at the end
+
+
+def test_compiled_in_limits_are_reported_not_truncated(built, tmp_path):
+    """A chain of more than GMR_MAXD (10) hinges, or more than 32 hinges, is refused with GMR_ELIMIT (-4) by the
+    same gmr_fill_consts that gmr_model_create runs; a 10-deep arm is accepted and solved."""
+    import ctypes as C
+    import helpers
+    from general_motion_retargeting_b200._native import build_desc
+    from general_motion_retargeting_b200.ik_config import IKConfig, compile_task_table
+    from general_motion_retargeting_b200.mjcf import load_mjcf
+
+    def chain_robot(n):
+        body = ""
+        for i in reversed(range(n)):
+            body = f'<body name="l{i}" pos="0 0 0.1"><joint name="j{i}" axis="{int(i % 2 == 0)} {int(i % 2 == 1)} 0" range="-1 1"/>{body}</body>'
+        xml = f'<mujoco><compiler angle="radian"/><worldbody><body name="base" pos="0 0 1"><freejoint/>{body}</body></worldbody></mujoco>'
+        p = tmp_path / f"chain{n}.xml"
+        p.write_text(xml)
+        m = load_mjcf(str(p))
+        ent = lambda frame, human: {frame: [human, 10, 5, [0, 0, 0], [1, 0, 0, 0]]}
+        table = {**ent("base", "root"), **ent(f"l{n - 1}", "tip")}
+        cfg = IKConfig.from_dict({"robot_root_name": "base", "human_root_name": "root", "ground_height": 0.0,
+                                  "human_height_assumption": 1.8, "use_ik_match_table1": True, "use_ik_match_table2": True,
+                                  "human_scale_table": {"root": 1.0, "tip": 1.0}, "ik_match_table1": table, "ik_match_table2": table})
+        return m, compile_task_table(m, cfg)
+
+    helpers.emu_retarget_batch(*chain_robot(2), np.zeros((1, 1, 2, 3), np.float32), np.tile([1, 0, 0, 0], (1, 1, 2, 1)).astype(np.float32), None)
+    emu = helpers._emu
+    for n, want in ((10, 0), (11, -4)):
+        m, tt = chain_robot(n)
+        desc, keep = build_desc(m, tt)
+        pos = np.zeros((1, 2, 2, 3), np.float32); pos[..., 1, 2] = 1.0 + 0.1 * n
+        quat = np.tile(np.array([1, 0, 0, 0], np.float32), (1, 2, 2, 1))
+        q = np.zeros((1, 2, m.nq))
+        rc = emu.gmr_emu_retarget_batch(C.byref(desc), C.c_void_p(pos.ctypes.data), C.c_void_p(quat.ctypes.data), None, 1, 2, None,
+                                        C.c_void_p(q.ctypes.data), None, None, None, 0, 1, 64, None)
+        assert rc == want, (n, rc)
+        if want == 0:
+            assert np.isfinite(q).all() and abs(np.linalg.norm(q[0, -1, 3:7]) - 1) < 1e-12
