@@ -66,7 +66,7 @@ struct GmrDims {
   int32_t o_tg, o_in, o_xp, o_xq, o_u, warp_elems;
   int32_t o_y, rs;            // published factor row of a hinge: slots [0, o_y), then y, 1/d, 2 pad; stride rs
 };
-template <typename R> struct GmrScal { R damping, lm, gain, tol, dt; };
+template <typename R> struct GmrScal { R damping, lm, gain, tol, dt, inv_dt; };
 
 template <typename R> inline GmrDims gmr_dims_of(const GmrConsts<R>& c) {
   GmrDims d;
@@ -78,7 +78,7 @@ template <typename R> inline GmrDims gmr_dims_of(const GmrConsts<R>& c) {
   return d;
 }
 template <typename R> inline GmrScal<R> gmr_scal_of(const GmrConsts<R>& c) {
-  GmrScal<R> s; s.damping = c.damping; s.lm = c.lm; s.gain = c.gain; s.tol = c.tol; s.dt = c.dt; return s;
+  GmrScal<R> s; s.damping = c.damping; s.lm = c.lm; s.gain = c.gain; s.tol = c.tol; s.dt = c.dt; s.inv_dt = R(1) / c.dt; return s;
 }
 
 // Validates `d` and fills `c`.  Returns GMR_OK or a negative GMR_E* code; `why` (may be null)

@@ -531,7 +531,7 @@ struct WarpSolver {
         // Jinv = I - S/2 + cV S^2, cV = (1 - (theta/2) cot(theta/2)) / theta^2 (also V^-1 of SE3.log)
         R cV;
         if (th2 < GmrEps<R>::lie) cV = R(1) / R(12);
-        else if (th2 < R(0.0625)) cV = R(1) / R(12) + th2 * (R(1) / R(720) + th2 * (R(1) / R(30240) + th2 / R(1209600)));   // series: the closed form cancels badly for small theta
+        else if (th2 < R(0.0625)) cV = R(1) / R(12) + th2 * (R(1) / R(720) + th2 * (R(1) / R(30240) + th2 * R(1.0 / 1209600.0)));   // series: the closed form cancels badly for small theta
         else cV = (R(1) - R(0.5) * g_sqrt(th2) * qe[0] / g_sqrt(nsq)) / th2;
         // rho = Jinv tb = tb - (omega x tb) / 2 + cV omega x (omega x tb)
         R c1[3] = {om[1] * tb[2] - om[2] * tb[1], om[2] * tb[0] - om[0] * tb[2], om[0] * tb[1] - om[1] * tb[0]};
@@ -561,9 +561,9 @@ struct WarpSolver {
           if (th2 < GmrEps<R>::lie) {
             Bq = R(1) / R(6); Cq = -R(1) / R(24); Dq = R(1) / R(120);
           } else if (th2 < R(0.0625)) {                    // series: the closed forms cancel badly for small theta
-            Bq = R(1) / R(6) - th2 * (R(1) / R(120) - th2 * (R(1) / R(5040) - th2 / R(362880)));
-            Cq = -R(1) / R(24) + th2 * (R(1) / R(720) - th2 * (R(1) / R(40320) - th2 / R(3628800)));
-            Dq = R(1) / R(120) - th2 * (R(1) / R(2520) - th2 * (R(1) / R(120960) - th2 / R(9979200)));
+            Bq = R(1) / R(6) - th2 * (R(1) / R(120) - th2 * (R(1) / R(5040) - th2 * R(1.0 / 362880.0)));
+            Cq = -R(1) / R(24) + th2 * (R(1) / R(720) - th2 * (R(1) / R(40320) - th2 * R(1.0 / 3628800.0)));
+            Dq = R(1) / R(120) - th2 * (R(1) / R(2520) - th2 * (R(1) / R(120960) - th2 * R(1.0 / 9979200.0)));
           } else {
             const R th = g_sqrt(th2);
             const R n = g_sqrt(nsq);                       // sin(theta/2); cw = cos(theta/2)
@@ -1027,10 +1027,12 @@ struct WarpSolver {
           if (lane < dm.nh) {
             const R x = lp(LP_X, lane);
             if (!((pinned >> lane) & 1u)) {
+              // step fraction to the first bound in the direction of the candidate; the division only happens for a
+              // lane that is actually blocked (al < 1  <=>  the remaining distance is shorter than the step)
               const R p = s_xs()[6 + lane] - x;
               const R bhi = bound_hi(lane), blo = bound_lo(lane);
-              if (p > R(0) && bhi < INF) al = (bhi - x) / p;
-              else if (p < R(0) && blo > -INF) al = (blo - x) / p;
+              if (p > R(0) && bhi < INF) { if (bhi - x < p) al = (bhi - x) / p; }
+              else if (p < R(0) && blo > -INF) { if (blo - x > p) al = (blo - x) / p; }
             } else {
               s_xs()[6 + lane] = x;                        // pinned: stays on its bound
             }
@@ -1155,25 +1157,28 @@ struct WarpSolver {
   // rotated into the root frame first.
   GMR_FN void integrate() {
     GMR_LANES
-      const R dt = ks.dt;
+      // v = dq / dt as a multiplication by the precomputed 1 / dt (a float64 division is ~20 instructions; the
+      // reference's round trip through dt only contributes rounding)
+      const R dt = ks.dt, idt = ks.inv_dt;
       if (lane < dm.nh) {
-        const R v = s_xs()[6 + lane] / dt;
+        const R v = s_xs()[6 + lane] * idt;
         s_q()[7 + lane] += dt * v;
       }
       if (lane == 0) {
         GMR_UNROLL
-        for (int i = 0; i < 3; i++) { const R v = s_xs()[i] / dt; s_q()[i] += dt * v; }
+        for (int i = 0; i < 3; i++) { const R v = s_xs()[i] * idt; s_q()[i] += dt * v; }
         R q[4]; g_ld4(s_rq(), q);                              // normalised root quaternion (s_xq is overwritten by the factor rows)
         R ww[3] = {s_xs()[3], s_xs()[4], s_xs()[5]}, wl[3];
         q_rot_inv(q, ww, wl);
-        R v[3] = {wl[0] / dt, wl[1] / dt, wl[2] / dt};
+        R v[3] = {wl[0] * idt, wl[1] * idt, wl[2] * idt};
         R nrm = g_sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
         R qr[4] = {R(1), R(0), R(0), R(0)};
         if (nrm >= R(1e-15)) {
           const R ang = dt * nrm;
           if (ang != R(0)) {
             R s, c; g_sincos(R(0.5) * ang, &s, &c);
-            qr[0] = c; qr[1] = v[0] / nrm * s; qr[2] = v[1] / nrm * s; qr[3] = v[2] / nrm * s;
+            const R k = s / nrm;
+            qr[0] = c; qr[1] = v[0] * k; qr[2] = v[1] * k; qr[3] = v[2] * k;
           }
         }
         R qq[4] = {s_q()[3], s_q()[4], s_q()[5], s_q()[6]};
