@@ -144,6 +144,8 @@ template <typename R> struct LaneRegs {
 // ---- tiny math helpers ----------------------------------------------------------------------
 template <typename R> GMR_FN R g_sqrt(R x) { return sqrt(x); }
 template <typename R> GMR_FN R g_atan2(R y, R x) { return atan2(y, x); }
+// square root of a strictly positive, normal-range argument (callers branch away from ~0 first)
+template <typename R> GMR_FN R g_sqrt_pos(R x) { return sqrt(x); }
 template <typename R> GMR_FN R g_abs(R x) { return fabs(x); }
 template <typename R> GMR_FN R g_rsqrt(R x) {
 #ifdef GMR_EMULATE
@@ -200,6 +202,22 @@ template <> __device__ __forceinline__ double g_rcp_pos<double>(double x) {
 #ifndef GMR_EMULATE
 template <> __device__ __forceinline__ float g_sqrt<float>(float x) { return sqrtf(x); }
 template <> __device__ __forceinline__ float g_rsqrt<float>(float x) { return rsqrtf(x); }
+// float64 1/sqrt for positive, normal-range arguments (pivots >= damping, squared quaternion norms): hardware seed
+// (~20 bits) + two Newton steps instead of the library routine with its special-case handling (~25 instructions,
+// six of them back to back on the base block's dependent chain)
+template <> __device__ __forceinline__ double g_rsqrt<double>(double x) {
+  double r; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double hx = 0.5 * x;
+  r = fma(r, fma(-hx * r, r, 0.5), r);
+  r = fma(r, fma(-hx * r, r, 0.5), r);
+  return r;
+}
+template <> __device__ __forceinline__ double g_sqrt_pos<double>(double x) {
+  const double r = g_rsqrt<double>(x);
+  const double s = x * r;
+  return fma(fma(-s, s, x), 0.5 * r, s);                 // one Heron correction
+}
+template <> __device__ __forceinline__ float g_sqrt_pos<float>(float x) { return sqrtf(x); }
 template <> __device__ __forceinline__ float g_atan2<float>(float y, float x) { return atan2f(y, x); }
 template <> __device__ __forceinline__ float g_abs<float>(float x) { return fabsf(x); }
 #endif
@@ -525,14 +543,14 @@ struct WarpSolver {
         const R nsq = qe[1] * qe[1] + qe[2] * qe[2] + qe[3] * qe[3];
         R fac;
         if (nsq < GmrEps<R>::lie) fac = R(2) / qe[0] - R(2) / R(3) * nsq / (qe[0] * qe[0] * qe[0]);
-        else { const R n = g_sqrt(nsq); fac = R(2) * g_atan2(n, qe[0]) / n; }
+        else { const R n = g_sqrt_pos(nsq); fac = R(2) * g_atan2(n, qe[0]) / n; }
         R om[3] = {fac * qe[1], fac * qe[2], fac * qe[3]};
         const R th2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
         // Jinv = I - S/2 + cV S^2, cV = (1 - (theta/2) cot(theta/2)) / theta^2 (also V^-1 of SE3.log)
         R cV;
         if (th2 < GmrEps<R>::lie) cV = R(1) / R(12);
         else if (th2 < R(0.0625)) cV = R(1) / R(12) + th2 * (R(1) / R(720) + th2 * (R(1) / R(30240) + th2 * R(1.0 / 1209600.0)));   // series: the closed form cancels badly for small theta
-        else cV = (R(1) - R(0.5) * g_sqrt(th2) * qe[0] / g_sqrt(nsq)) / th2;
+        else cV = (R(1) - R(0.5) * g_sqrt_pos(th2) * qe[0] / g_sqrt_pos(nsq)) / th2;
         // rho = Jinv tb = tb - (omega x tb) / 2 + cV omega x (omega x tb)
         R c1[3] = {om[1] * tb[2] - om[2] * tb[1], om[2] * tb[0] - om[0] * tb[2], om[0] * tb[1] - om[1] * tb[0]};
         R c2[3] = {om[1] * c1[2] - om[2] * c1[1], om[2] * c1[0] - om[0] * c1[2], om[0] * c1[1] - om[1] * c1[0]};
