@@ -360,3 +360,27 @@ def test_two_phase_schedule_is_invisible(lib, torch_cuda):
     q, it, err = g.retarget_batch(pos, quat, h, return_info=True)
     qs, its, errs = g.retarget_batch(pos[idx], quat[idx], h[idx], return_info=True)
     assert torch.equal(q[idx], qs) and torch.equal(it[idx], its) and torch.equal(err[idx], errs)
+
+
+def test_host_entry_on_a_two_phase_batch_matches_device_path(lib, torch_cuda):
+    """gmr_retarget_batch_host on a batch large enough for the two-phase schedule (one chunk: copy in, two-phase
+    solve, copy out).  Same numbers as the device-resident entry (float32 buffers, float64 arithmetic), iteration
+    counts and errors included."""
+    torch = torch_cuda
+    from general_motion_retargeting_b200 import GeneralMotionRetargeting
+    m, tt, _ = problem("smplx", "unitree_g1")
+    Cn, T = 1300, 130
+    clips = make_clips(m, tt, range(300, 300 + Cn), T=T, device="cuda")
+    g = GeneralMotionRetargeting("smplx", "unitree_g1")
+    qh, ith, errh = g.retarget_batch(clips.pos, clips.quat, clips.heights, return_info=True)              # numpy -> host pipeline
+    assert qh.dtype == np.float32 and qh.shape == (Cn, T, m.nq)
+    qd, itd, errd = g.retarget_batch(torch.from_numpy(clips.pos).cuda(), torch.from_numpy(clips.quat).cuda(),
+                                     torch.from_numpy(clips.heights).cuda(), return_info=True)          # float64 buffers on the device
+    np.testing.assert_array_equal(ith, itd.cpu().numpy())
+    np.testing.assert_allclose(qh, qd.cpu().numpy(), atol=2e-6)                                          # float32 rounding of the output only
+    np.testing.assert_allclose(errh, errd.cpu().numpy(), rtol=1e-6, atol=1e-6)
+    # float32 arithmetic through the same pipeline is bit-identical to the float32 device entry
+    qh32 = g.retarget_batch(clips.pos, clips.quat, clips.heights, precision="f32")
+    qd32 = g.retarget_batch(torch.from_numpy(clips.pos).cuda(), torch.from_numpy(clips.quat).cuda(),
+                            torch.from_numpy(clips.heights).cuda(), precision="f32")
+    np.testing.assert_array_equal(qh32, qd32.cpu().numpy())
