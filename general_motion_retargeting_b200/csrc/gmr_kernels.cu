@@ -3,8 +3,11 @@
 // One persistent CTA per SM, one warp per clip (gmr_solver.cuh).  The per-robot constant
 // block is staged once per CTA into shared memory (one TMA bulk copy, cp.async.bulk, issued
 // by an elected thread and awaited on an mbarrier); per-warp solver state follows it in the
-// same dynamic allocation.  Work is sharded by clip with no inter-warp communication, so the
-// grid is sized to the SM count and warps stride over clips.
+// same dynamic allocation.  Work is sharded by clip with no inter-warp communication: the grid is
+// sized to the SM count and warps take clips from a global queue; launch() orders the queue (hard
+// clips first) or, for batches of 1-4 waves, runs the two-phase schedule (frame 0 -> classify ->
+// the rest with slow clips on their own SMs), see DESIGN.md "Clip scheduling".  Also here: the
+// motion-array epilogue kernel, the human-frame producers (gmr_producers.cuh) and the live stream.
 #include <cuda_runtime.h>
 
 #include <atomic>

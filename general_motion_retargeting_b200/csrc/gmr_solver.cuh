@@ -6,23 +6,25 @@
 // scripts/smplx_to_robot_dataset.py:84-87).  This is NOT a port of the mink/MuJoCo/DAQP
 // call sequence; the per-solve algebra is re-derived for a 32-lane warp:
 //
-//  * FK by tree level (lanes = bodies of one depth), positions kept relative to the
-//    floating root so float32 keeps ~1e-7 m resolution anywhere in the world.
+//  * FK by tree level (lanes = bodies of one depth) from packed per-body records, positions kept
+//    relative to the floating root so float32 keeps ~1e-7 m resolution anywhere in the world.
 //  * The QP matrix H = damping*I + sum_t [(W J_t)^T (W J_t) + mu_t I] is never formed from
 //    dense 6 x nv task Jacobians.  Each frame task is a 6x6 "spring inertia"
 //    M_t = A_t^T A_t at the reference point (A_t = -W * Jlog_t * blkdiag(R_b^T) shifted to the
-//    root), every hinge lane sums the M_t of the tasks in its subtree (composite, as in the
-//    composite-rigid-body algorithm) and gets its row as H_ij = s_i^T Ic_i s_j over its
-//    ancestors j, with s_j the world-frame spatial axis of DoF j.  ~10x fewer flops than the
-//    dense J^T W^2 J and no shared-memory read-modify-write.
-//  * Row i of H lives in REGISTERS of lane i (static indexing, loops unrolled over the pivot
-//    index); the Cholesky factorisation broadcasts the pivot row from shared memory
-//    (one 128-bit wavefront per 4 values) instead of shuffling or re-reading lane-private
-//    rows.  The 6 floating-base DoFs form a 6x6 leading block, so no lane ever needs a
-//    second pass when nv = 6 + nhinge > 32.
+//    root); the M_t are summed leaf-to-root over the task tree, every hinge lane takes the
+//    composite of its subtree (as in the composite-rigid-body algorithm) and gets its row as
+//    H_ij = s_i^T Ic_i s_j over its ancestors j, with s_j the world-frame spatial axis of DoF j.
+//    ~10x fewer flops than the dense J^T W^2 J and no shared-memory read-modify-write.
+//  * H_ij is non-zero only between a hinge and its ancestors (branch-induced sparsity).  Row i
+//    lives in REGISTERS of lane i, indexed by the DEPTH of the ancestor (6 floating-base slots, then
+//    <= GMR_MAXD - 1 ancestors): every hinge of a root-to-leaf chain sees the same ancestor at the
+//    same slot, so all register indices are static.  The factorisation is a branch-sparse L^T D L
+//    that eliminates hinges by depth, leaves first (no fill-in): the hinges of one depth publish
+//    their rows to shared memory, their ancestors absorb them; the floating base is the 6x6 Schur
+//    complement of everything, accumulated by 27 lanes in the same loop.
 //  * Joint-limit box: exact primal active set (same optimum as the reference's DAQP solve),
-//    working set warm-started from the previous solve; the common case (unconstrained step
-//    feasible) costs one factorisation.
+//    working set kept per stage and warm-started from the previous solve; the common case
+//    (unconstrained step feasible) costs one factorisation.
 //
 // The file is written as a sequence of "lane blocks" (GMR_LANES ... GMR_END).  On the GPU a
 // block is straight-line code of one thread followed by __syncwarp(); defining GMR_EMULATE
