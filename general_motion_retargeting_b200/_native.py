@@ -96,6 +96,13 @@ class GmrBatchExtra(C.Structure):
                 ("warm_state", C.c_void_p)]
 
 
+class GmrBatchDesc(C.Structure):
+    """Mirror of the C struct: one robot-uniform bucket of a mixed-robot launch (device pointers as integers)."""
+    _fields_ = [("model", C.c_void_p), ("pos", C.c_void_p), ("quat", C.c_void_p), ("ratio", C.c_void_p),
+                ("C", C.c_int32), ("T", C.c_int32), ("qpos_init", C.c_void_p), ("qpos_out", C.c_void_p),
+                ("iters_out", C.c_void_p), ("err_out", C.c_void_p)]
+
+
 class NativeLibraryMissing(RuntimeError):
     pass
 
@@ -147,6 +154,8 @@ def load_library() -> C.CDLL:
     lib.gmr_produce_smplx_frames.argtypes = [f32p, f32p, f32p, i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, i32p, C.c_int32,
                                              f32p, f32p, vp]
     lib.gmr_produce_smplx_frames.restype = C.c_int
+    lib.gmr_retarget_multi.argtypes = [C.POINTER(GmrBatchDesc), C.c_int32, C.c_uint32, vp]
+    lib.gmr_retarget_multi.restype = C.c_int
     lib.gmr_launch_count.argtypes = []
     lib.gmr_launch_count.restype = C.c_int64
     lib.gmr_last_error.argtypes = []
@@ -162,5 +171,5 @@ EXPORTED_SYMBOLS = [
     "gmr_retarget_batch_host", "gmr_launch_count", "gmr_last_error", "gmr_kernel_info",
     "gmr_retarget_batch_ex", "gmr_finalize_motion",
     "gmr_stream_create", "gmr_stream_destroy", "gmr_stream_reset", "gmr_stream_retarget",
-    "gmr_produce_bvh_frames", "gmr_produce_smplx_frames",
+    "gmr_produce_bvh_frames", "gmr_produce_smplx_frames", "gmr_retarget_multi",
 ]

@@ -203,6 +203,60 @@ gmr_finalize_kernel(const float* __restrict__ qpos, const float* __restrict__ lo
 }
 
 constexpr int QUEUE_RING = 256;
+// Mixed-robot batches (BASELINE.json configs[4]): ONE launch serves up to GMR_MAX_MULTI robot-uniform buckets.  The
+// CTAs are divided among the buckets in proportion to their work; a CTA stages its bucket's constant block and
+// copies the bucket's dims / scalars / batch pointers from the kernel parameters into shared memory (they cannot
+// be compile-time constant-bank operands here, which costs a few per cent per solve), then serves its bucket's
+// clip queue.  Running the buckets as separate launches instead makes their tails add up (one CTA per SM).
+#define GMR_MAX_MULTI 8
+template <typename R, typename IO> struct GmrMultiArgs {
+  int32_t n, _pad[3];
+  int32_t cta_end[GMR_MAX_MULTI];                  // CTAs [cta_end[r-1], cta_end[r]) serve bucket r
+  GmrDims dm[GMR_MAX_MULTI];
+  GmrScal<R> ks[GMR_MAX_MULTI];
+  const GmrConsts<R>* gc[GMR_MAX_MULTI];
+  GmrIO<IO> io[GMR_MAX_MULTI];
+  int* queue[GMR_MAX_MULTI];                       // {next position, n_hard, n_easy, -}
+  const int* order[GMR_MAX_MULTI];                 // hard-first permutation or null
+};
+struct MultiLocal { GmrDims dm; int32_t r, cta_begin, cta_count, _pad; };
+
+template <typename R, typename IO, int MAXWARPS>
+__global__ void __launch_bounds__(MAXWARPS * 32, 1)
+gmr_retarget_multi_kernel(const __grid_constant__ GmrMultiArgs<R, IO> mu) {
+  extern __shared__ __align__(128) unsigned char gmr_dyn_smem[];
+  unsigned char* const smem = gmr_dyn_smem;
+  constexpr int CB = consts_bytes<R>();
+  constexpr int LB = (int)((sizeof(MultiLocal) + sizeof(GmrScal<R>) + sizeof(GmrIO<IO>) + 15) / 16 * 16);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  GmrConsts<R>* mc = reinterpret_cast<GmrConsts<R>*>(smem + 16);
+  MultiLocal* loc = reinterpret_cast<MultiLocal*>(smem + 16 + CB);
+  GmrScal<R>* ks = reinterpret_cast<GmrScal<R>*>(smem + 16 + CB + sizeof(MultiLocal));
+  GmrIO<IO>* io = reinterpret_cast<GmrIO<IO>*>(smem + 16 + CB + sizeof(MultiLocal) + sizeof(GmrScal<R>));
+  int r = 0;
+  while (r + 1 < mu.n && (int)blockIdx.x >= mu.cta_end[r]) r++;
+  if (threadIdx.x == 0) {
+    loc->dm = mu.dm[r]; loc->r = r; loc->cta_begin = r ? mu.cta_end[r - 1] : 0; loc->cta_count = mu.cta_end[r] - loc->cta_begin;
+    *ks = mu.ks[r]; *io = mu.io[r];
+  }
+  stage_consts_tma(mc, mu.gc[r], CB, bar);                             // contains the __syncthreads that publishes the copies above
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  const GmrDims& dm = loc->dm;
+  WarpSolver<R> ws(*mc, dm, *ks, (uint32_t)(16 + CB + LB) + (uint32_t)warp * (uint32_t)dm.warp_elems * (uint32_t)sizeof(R), lane);
+  const int C = io->C, lb = (int)blockIdx.x - loc->cta_begin, lg = loc->cta_count;
+  int* queue = mu.queue[r];
+  const int* order = mu.order[r];
+  const int nw = lg * wpc;
+  const int n_hard = order ? queue[1] : 0;
+  for (int p = warp * lg + lb; p < C;) {
+    const int c = order ? (p < n_hard ? order[p] : order[C + p - n_hard]) : p;
+    ws.template run_clip<IO>(*io, c);
+    int nxt = 0;
+    if (lane == 0) nxt = nw + atomicAdd(queue, 1);
+    p = __shfl_sync(0xffffffffu, nxt, 0);
+  }
+}
+
 constexpr int MAXW_F32 = 28;   // 28 warps * 32 lanes * 72 registers = one SM's register file
 constexpr int MAXW_F64 = 16;   // 16 warps * 32 lanes * 128 registers
 
@@ -478,6 +532,95 @@ int gmr_finalize_motion(GmrModel* m, const float* qpos, const float* lowest_z, c
   g_launches.fetch_add(1);
   CK(cudaGetLastError());
   return GMR_OK;
+}
+
+}  // extern "C"
+
+namespace {
+template <typename R, int MAXWARPS>
+int launch_multi(const GmrBatchDesc* b, int n, uint32_t flags, cudaStream_t st) {
+  GmrModel* m0 = b[0].model;
+  auto kern = gmr_retarget_multi_kernel<R, float, MAXWARPS>;
+  constexpr int LB = (int)((sizeof(MultiLocal) + sizeof(GmrScal<R>) + sizeof(GmrIO<float>) + 15) / 16 * 16);
+  // warps per CTA: what the largest robot's state allows; CTAs: the device's SMs, split by work (clips x frames)
+  int wel = 0;
+  double work_total = 0;
+  for (int i = 0; i < n; i++) {
+    const int w = sizeof(R) == 4 ? b[i].model->wel32 : b[i].model->wel64;
+    if (w > wel) wel = w;
+    work_total += (double)b[i].C * b[i].T;
+  }
+  int wpc = max_warps<R>();
+  while (wpc > 1 && 16 + (size_t)consts_bytes<R>() + LB + (size_t)wpc * wel * sizeof(R) > (size_t)m0->max_smem) wpc--;
+  const size_t smem = 16 + (size_t)consts_bytes<R>() + LB + (size_t)wpc * wel * sizeof(R);
+  if (smem > (size_t)m0->max_smem) return set_err(GMR_ELIMIT, "models do not fit in shared memory");
+  static std::atomic<uint64_t> configured{0};
+  const uint64_t dev_bit = 1ull << (m0->device & 63);
+  if (!(configured.load(std::memory_order_acquire) & dev_bit)) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m0->max_smem));
+    configured.fetch_or(dev_bit, std::memory_order_release);
+  }
+  const int grid = m0->num_sms;
+  if (grid < n) return set_err(GMR_ELIMIT, "more buckets than SMs");
+  GmrMultiArgs<R, float> mu{};
+  mu.n = n;
+  StreamScratch scratch(st);
+  size_t order_ints = 0;
+  for (int i = 0; i < n; i++) order_ints += (size_t)2 * b[i].C;
+  CK(scratch.alloc(order_ints * sizeof(int)));
+  int* order_base = reinterpret_cast<int*>(scratch.p);
+  int assigned = 0;
+  double acc = 0;
+  for (int i = 0; i < n; i++) {
+    GmrModel* m = b[i].model;
+    acc += (double)b[i].C * b[i].T;
+    int end = i + 1 == n ? grid : (int)(grid * (acc / work_total) + 0.5);
+    if (end < assigned + 1) end = assigned + 1;                       // at least one CTA per bucket
+    if (end > grid - (n - 1 - i)) end = grid - (n - 1 - i);
+    mu.cta_end[i] = end;
+    assigned = end;
+    mu.dm[i] = sizeof(R) == 4 ? m->dims32 : m->dims64;
+    mu.ks[i] = scal_of<R>(m);
+    mu.gc[i] = sizeof(R) == 4 ? reinterpret_cast<const GmrConsts<R>*>(m->d_f32) : reinterpret_cast<const GmrConsts<R>*>(m->d_f64);
+    GmrIO<float>& io = mu.io[i];
+    io.pos = b[i].pos; io.quat = b[i].quat; io.ratio = b[i].ratio; io.qinit = b[i].qpos_init; io.qout = b[i].qpos_out;
+    io.iters = b[i].iters_out; io.err = b[i].err_out; io.tg = nullptr; io.C = b[i].C; io.T = b[i].T; io.flags = flags & 0xffffu;
+    int* q = m0->d_queue + 4 * (m0->queue_next.fetch_add(1) % QUEUE_RING);
+    CK(cudaMemsetAsync(q, 0, 4 * sizeof(int), st));
+    mu.queue[i] = q;
+    // hard clips first within each bucket (same pre-pass as the single-robot path)
+    gmr_order_kernel<R, float><<<(b[i].C + 255) / 256, 256, 0, st>>>(mu.gc[i], b[i].quat, b[i].qpos_init, b[i].C, b[i].T, q + 1, order_base);
+    CK(cudaGetLastError());
+    mu.order[i] = order_base;
+    order_base += (size_t)2 * b[i].C;
+    g_launches.fetch_add(1);
+  }
+  kern<<<grid, wpc * 32, smem, st>>>(mu);
+  g_launches.fetch_add(1);
+  CK(cudaGetLastError());
+  return GMR_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int gmr_retarget_multi(const GmrBatchDesc* batches, int32_t n, uint32_t flags, void* cuda_stream) {
+  if (n < 0 || (n > 0 && !batches)) return set_err(GMR_EINVAL, "bad bucket list");
+  if (n == 0) return GMR_OK;
+  if (n > GMR_MAX_MULTI) return set_err(GMR_ELIMIT, "more than 8 buckets in one launch");
+  if (flags & GMR_FLAG_NO_SOLVE) return set_err(GMR_EINVAL, "GMR_FLAG_NO_SOLVE is not supported by gmr_retarget_multi");
+  for (int i = 0; i < n; i++) {
+    const GmrBatchDesc& d = batches[i];
+    if (!d.model) return set_err(GMR_EINVAL, "model is null");
+    if (d.model->device != batches[0].model->device) return set_err(GMR_EINVAL, "all buckets must live on one device");
+    if (d.C <= 0 || d.T <= 0) return set_err(GMR_EINVAL, "empty bucket");
+    if (!d.pos || !d.quat || !d.qpos_out) return set_err(GMR_EINVAL, "pos, quat and qpos_out are required");
+    if ((reinterpret_cast<uintptr_t>(d.quat) & 15u) != 0) return set_err(GMR_EINVAL, "quat must be 16-byte aligned");
+  }
+  DeviceGuard g(batches[0].model->device);
+  if (!g.ok) return set_err(GMR_ECUDA, "cannot select the models' device");
+  if (flags & GMR_FLAG_COMPUTE_F64) return launch_multi<double, MAXW_F64>(batches, n, flags, (cudaStream_t)cuda_stream);
+  return launch_multi<float, MAXW_F32>(batches, n, flags, (cudaStream_t)cuda_stream);
 }
 
 // ---- single live stream ---------------------------------------------------------------------------------

@@ -485,3 +485,46 @@ class GeneralMotionRetargeting:
 
         with ThreadPoolExecutor(max_workers=max(1, workers)) as ex:
             list(ex.map(one, zip(motions, paths)))
+
+
+def retarget_mixed(buckets, precision: str = "f64", return_info: bool = False):
+    """Mixed-robot batches (BASELINE.json configs[4]) in ONE launch: `buckets` is a list of
+    ``(retargeter, pos [C,T,nh,3], quat [C,T,nh,4], heights [C] or None)`` with torch CUDA tensors on one device, one
+    entry per robot (group the clips with `sharding.bucket_by_robot`).  The device's SMs are divided among the
+    buckets by work, so a bucket's slow clips overlap the other buckets' bulk instead of every bucket paying its own
+    tail.  Each clip is solved exactly as by `retargeter.retarget_batch`.  Returns the list of qpos tensors
+    ([C,T,nq] float32), with `return_info` also the per-frame iteration counts."""
+    import torch
+    if precision not in ("f32", "f64"):
+        raise ValueError("precision must be 'f32' or 'f64'")
+    if not buckets:
+        return []
+    lib = buckets[0][0]._lib
+    dev = buckets[0][1].device
+    descs = (_native.GmrBatchDesc * len(buckets))()
+    keep, outs, iters = [], [], []
+    with torch.cuda.device(dev):
+        for k, (g, pos, quat, heights) in enumerate(buckets):
+            if not (_is_torch(pos) and pos.is_cuda and pos.device == dev):
+                raise ValueError("retarget_mixed takes torch CUDA tensors on one device")
+            nq, nh = g._robot.nq, g._table.nh
+            Cn, T = int(pos.shape[0]), int(pos.shape[1])
+            if tuple(pos.shape[2:]) != (nh, 3) or tuple(quat.shape) != (Cn, T, nh, 4):
+                raise ValueError(f"bucket {k}: expected pos [C,T,{nh},3] and quat [C,T,{nh},4]")
+            d_pos = pos.to(torch.float32).contiguous(); d_quat = quat.to(dev, torch.float32).contiguous()
+            if heights is None:
+                d_ratio = torch.full((Cn,), g._ratio, dtype=torch.float32, device=dev)
+            else:
+                d_ratio = (torch.as_tensor(heights, device=dev).to(torch.float64) / float(g._cfg.human_height_assumption)).to(torch.float32).contiguous()
+            d_q = torch.empty((Cn, T, nq), dtype=torch.float32, device=dev)
+            d_it = torch.zeros((Cn, T, 2), dtype=torch.int32, device=dev) if return_info else None
+            h = g._handle(dev.index if dev.index is not None else torch.cuda.current_device())
+            keep += [d_pos, d_quat, d_ratio, h]
+            descs[k] = _native.GmrBatchDesc(h.ptr.value, d_pos.data_ptr(), d_quat.data_ptr(), d_ratio.data_ptr(), Cn, T, None,
+                                            d_q.data_ptr(), None if d_it is None else d_it.data_ptr(), None)
+            outs.append(d_q); iters.append(d_it)
+        flags = FLAG_COMPUTE_F64 if precision == "f64" else 0
+        rc = lib.gmr_retarget_multi(descs, len(buckets), flags, torch.cuda.current_stream(dev).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"gmr_retarget_multi failed ({rc}): {lib.gmr_last_error().decode()}")
+    return (outs, iters) if return_info else outs

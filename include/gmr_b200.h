@@ -123,6 +123,20 @@ int gmr_retarget_batch_ex(GmrModel* model, const float* pos, const float* quat, 
                           int32_t* iters_out, float* err_out, float* targets_out,
                           const GmrBatchExtra* extra, uint32_t flags, void* cuda_stream);
 
+/* Mixed-robot batches (BASELINE.json configs[4]: clips of several robots retargeted together).  A launch is
+ * robot-uniform per CTA, so the caller groups the clips by robot ("buckets", one model handle each) and hands all
+ * buckets to ONE call: the device's SMs are divided among the buckets by work and every bucket's slow clips overlap
+ * with the other buckets' bulk (separate gmr_retarget_batch calls would serialise their tails).  float32 buffers,
+ * flags: GMR_FLAG_COMPUTE_F64, GMR_FLAG_OFFSET_TO_GROUND.  At most 8 buckets, all on one device. */
+typedef struct GmrBatchDesc {
+  GmrModel* model;
+  const float* pos; const float* quat; const float* ratio;   /* as gmr_retarget_batch */
+  int32_t C, T;
+  const float* qpos_init;                                     /* or NULL */
+  float* qpos_out; int32_t* iters_out; float* err_out;        /* iters_out / err_out may be NULL */
+} GmrBatchDesc;
+int gmr_retarget_multi(const GmrBatchDesc* batches, int32_t n, uint32_t flags, void* cuda_stream);
+
 /* The rest of the scripts' epilogue as one elementwise pass (replaces :97-131 / :112-143): splits qpos into
  * the arrays the motion pkl holds (consumers: data_loader.py:4-16, booster_gym/utils/motion_loader.py:42-100),
  *   root_pos [C,T,3], root_rot [C,T,4] xyzw (:103-104), dof_pos [C,T,nhinge]            (all float32, device)

@@ -384,3 +384,32 @@ def test_host_entry_on_a_two_phase_batch_matches_device_path(lib, torch_cuda):
     qd32 = g.retarget_batch(torch.from_numpy(clips.pos).cuda(), torch.from_numpy(clips.quat).cuda(),
                             torch.from_numpy(clips.heights).cuda(), precision="f32")
     np.testing.assert_array_equal(qh32, qd32.cpu().numpy())
+
+
+def test_mixed_robot_launch_equals_per_robot_batches(lib, torch_cuda):
+    """gmr_retarget_multi: several robot-uniform buckets in one launch (BASELINE.json configs[4]); every clip is
+    solved exactly as by its own robot's retarget_batch (float32 buffers, float64 arithmetic), also with more
+    clips than warp slots per bucket."""
+    torch = torch_cuda
+    from general_motion_retargeting_b200 import GeneralMotionRetargeting, retarget_mixed
+    specs = [("smplx", "unitree_g1", 37), ("smplx", "booster_t1", 5), ("bvh", "fourier_n1", 160), ("smplx", "engineai_pm01", 1),
+             ("smplx", "hightorque_hi", 23)]
+    buckets, refs = [], []
+    for k, (src, robot, n) in enumerate(specs):
+        m, tt, _ = problem(src, robot)
+        clips = make_clips(m, tt, range(100 * k, 100 * k + n), T=14, src_human=src)
+        g = GeneralMotionRetargeting(src, robot, device=0)
+        pos, quat, h = torch.from_numpy(clips.pos).cuda(), torch.from_numpy(clips.quat).cuda(), torch.from_numpy(clips.heights).cuda()
+        buckets.append((g, pos, quat, h))
+        q = g.retarget_batch(clips.pos, clips.quat, clips.heights, return_info=True)          # host entry: float32 buffers, f64 arithmetic
+        refs.append(q)
+    outs, iters = retarget_mixed(buckets, return_info=True)
+    torch.cuda.synchronize()
+    for (q_ref, it_ref, _), q, it in zip(refs, outs, iters):
+        np.testing.assert_array_equal(it.cpu().numpy(), it_ref)
+        np.testing.assert_array_equal(q.cpu().numpy(), q_ref)
+    outs32 = retarget_mixed(buckets, precision="f32")
+    q32 = buckets[2][0].retarget_batch(buckets[2][1], buckets[2][2], buckets[2][3], precision="f32")
+    assert torch.equal(outs32[2], q32)
+    with pytest.raises(RuntimeError):
+        retarget_mixed(buckets * 2)                                                             # 10 buckets > 8
