@@ -25,6 +25,8 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
+METRIC = "retargeted frames/sec (G1 29-DoF)"       # BASELINE.json's metric, quoted on configs[1]
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -157,7 +159,7 @@ def main_reference(args):
     tot = sum(times)
     value = sample * args.frames * args.steps / tot
     line = {
-        "metric": "retargeted frames/sec (G1 29-DoF)", "value": value, "unit": "frames/s", "impl": "reference",
+        "metric": METRIC if args.robot == "unitree_g1" else f"retargeted frames/sec ({args.robot})", "value": value, "unit": "frames/s", "impl": "reference",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.robot} ({args.src}), {sample} synthetic clips x {args.frames} frames per step "
@@ -352,14 +354,14 @@ def main_ours(args):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         line = {
-            "metric": "retargeted frames/sec (G1 29-DoF)", "value": value, "unit": "frames/s",
+            "metric": METRIC if args.robot == "unitree_g1" else f"retargeted frames/sec ({args.robot})", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"{args.robot} ({args.src} mapping), {C} synthetic clips x {T} frames per GPU, "
                                    "sequential two-stage IK warm-started per clip (BASELINE.json configs[1])",
                        "clips_per_gpu": C, "frames": T, "sharding": "clips, contiguous ranges per rank, no collective",
-                       "l2": f"inputs {(clips.pos.nbytes + clips.quat.nbytes) / 1e6:.0f} MB per step > 126 MB L2",
+                       "l2": (lambda mb: f"inputs {mb:.0f} MB per step {'>' if mb > 126 else '<= (reduced-size run: L2 not flushed)'} 126 MB L2")((clips.pos.nbytes + clips.quat.nbytes) / 1e6),
                        "solves_per_frame": float(iters.sum() / (C * T))},
             "gpu_launches": int(launches),
             "clocks": clocks,
