@@ -364,7 +364,11 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
   auto next_queue = [&]() { return m->d_queue + 4 * (m->queue_next.fetch_add(1) % QUEUE_RING); };
   const int slots = grid * wpc;
   static const int lpt_env = getenv("GMR_LPT") ? atoi(getenv("GMR_LPT")) : 1;
-  static const int part_env = getenv("GMR_PARTITION") ? atoi(getenv("GMR_PARTITION")) : 4;   // warps per slow SM, 0 = off
+  // warps per slow SM (0 = off) and share of the SMs the slow clips may take: measured optima on the benchmark mix
+  // (tools/prof/mix_case.py, ~10 % of the clips classified slow).  float32: 4 warps / 55 % (64 ms vs 70 ms at 40 %,
+  // worse beyond 65 %).  float64 has 16 instead of 28 warps per SM to give away, so sparse slow SMs cost it more
+  // capacity: 6 warps / 45 % (82 ms vs 86 ms at 4 / 55 % and 88-90 ms at 8-10 warps / 30-35 %).
+  static const int part_env = getenv("GMR_PARTITION") ? atoi(getenv("GMR_PARTITION")) : (sizeof(R) == 8 ? 6 : 4);
 
   // ---- batches of ~1-4 waves: frame 0 for every clip, classify, then the rest with slow clips on their own SMs ----
   const bool two_phase = part_env > 0 && !own_queue && !convoy && !(flags & GMR_FLAG_NO_SOLVE) && T >= 16 &&
@@ -390,9 +394,7 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
     // launch B: frames 1 .. T-1, partitioned
     GmrIO<IO> iob = io;
     iob.t_begin = 1; iob.t_end = 0; iob.state = state;
-    // share of the SMs the slow clips may take: measured optimum on the benchmark mix (tools/prof/mix_case.py), where
-    // ~10 % of the clips are classified slow: 55 % (f32 64 ms vs 70 ms at 40 %; f64 flat between 40 and 55 %)
-    static const int pct_env = getenv("GMR_PARTITION_PCT") ? atoi(getenv("GMR_PARTITION_PCT")) : 55;
+    static const int pct_env = getenv("GMR_PARTITION_PCT") ? atoi(getenv("GMR_PARTITION_PCT")) : (sizeof(R) == 8 ? 45 : 55);
     kern<<<grid, wpc * 32, smem, st>>>(dims, scal_of<R>(m), dc, iob, flags, q2, order2, part_env, pct_env);
     CK(cudaGetLastError());
     g_launches.fetch_add(3);
