@@ -2,7 +2,7 @@
 from .params import (IK_CONFIG_DICT, ROBOT_BASE_DICT, ROBOT_XML_DICT,  # noqa: F401
                      VIEWER_CAM_DISTANCE_DICT)
 
-__all__ = ["GeneralMotionRetargeting", "retarget_mixed", "ROBOT_XML_DICT", "IK_CONFIG_DICT",
+__all__ = ["GeneralMotionRetargeting", "RetargetFailure", "retarget_mixed", "ROBOT_XML_DICT", "IK_CONFIG_DICT",
            "ROBOT_BASE_DICT", "VIEWER_CAM_DISTANCE_DICT"]
 
 
@@ -12,6 +12,9 @@ def __getattr__(name):
     if name == "GeneralMotionRetargeting":
         from .motion_retarget import GeneralMotionRetargeting
         return GeneralMotionRetargeting
+    if name == "RetargetFailure":
+        from .motion_retarget import RetargetFailure
+        return RetargetFailure
     if name == "retarget_mixed":
         from .motion_retarget import retarget_mixed
         return retarget_mixed

@@ -21,6 +21,12 @@ LIB_PATH = HERE / "csrc" / "libgmr_b200.so"
 
 GMR_MAX_BODY, GMR_MAX_HINGE, GMR_MAX_HUMAN, GMR_MAX_TASK = 64, 32, 32, 32
 GMR_FLAG_OFFSET_TO_GROUND = 1
+GMR_STATUS_BAD_INPUT, GMR_STATUS_AS_CAP, GMR_STATUS_NONFINITE = 1, 2, 4
+GMR_STATUS_FATAL = GMR_STATUS_BAD_INPUT | GMR_STATUS_NONFINITE
+# mink.lie.utils.get_epsilon(float64) as recalled from upstream (not stated in the reference tree); round 1 assumed
+# LIE_EPS_ROUND1.  A model parameter, see GmrModelDesc.lie_eps.
+LIE_EPS_DEFAULT = 1e-10
+LIE_EPS_ROUND1 = 2.220446049250313e-15
 
 _pd = C.POINTER(C.c_double)
 _pi = C.POINTER(C.c_int32)
@@ -40,12 +46,15 @@ class GmrModelDesc(C.Structure):
         ("use_stage1", C.c_int32), ("use_stage2", C.c_int32),
         ("damping", C.c_double), ("lm_damping", C.c_double), ("limit_gain", C.c_double),
         ("tol", C.c_double), ("timestep", C.c_double), ("max_iter", C.c_int32),
+        ("lie_eps", C.c_double),
     ]
 
 
 def build_desc(robot: RobotModel, table: TaskTable, damping: float = 0.5, lm_damping: float = 1.0,
-               limit_gain: float = 0.95, tol: float = 1e-3, max_iter: int = 10) -> Tuple[GmrModelDesc, List[np.ndarray]]:
-    """Returns (desc, keepalive): the arrays in `keepalive` back the struct's pointers."""
+               limit_gain: float = 0.95, tol: float = 1e-3, max_iter: int = 10,
+               lie_eps: float = 0.0) -> Tuple[GmrModelDesc, List[np.ndarray]]:
+    """Returns (desc, keepalive): the arrays in `keepalive` back the struct's pointers.
+    `lie_eps`: mink's small-angle threshold (0 = LIE_EPS_DEFAULT, see include/gmr_b200.h)."""
     keep: List[np.ndarray] = []
 
     def arr(a, dtype):
@@ -87,13 +96,14 @@ def build_desc(robot: RobotModel, table: TaskTable, damping: float = 0.5, lm_dam
     d.use_stage1, d.use_stage2 = int(table.use1), int(table.use2)
     d.damping, d.lm_damping, d.limit_gain = float(damping), float(lm_damping), float(limit_gain)
     d.tol, d.timestep, d.max_iter = float(tol), float(robot.timestep), int(max_iter)
+    d.lie_eps = float(lie_eps) if lie_eps and lie_eps > 0 else LIE_EPS_DEFAULT
     return d, keep
 
 
 class GmrBatchExtra(C.Structure):
     """Mirror of the C struct (device pointers as integers; 0 = NULL)."""
     _fields_ = [("lengths", C.c_void_p), ("local_body_pos", C.c_void_p), ("lowest_z", C.c_void_p),
-                ("warm_state", C.c_void_p)]
+                ("warm_state", C.c_void_p), ("status", C.c_void_p)]
 
 
 class GmrBatchDesc(C.Structure):
@@ -132,9 +142,15 @@ def load_library() -> C.CDLL:
     lib.gmr_retarget_batch_f64.argtypes = [vp, f32p, f32p, f32p, C.c_int32, C.c_int32, f64p, f64p, i32p, f64p, f64p,
                                            C.c_uint32, vp]
     lib.gmr_retarget_batch_f64.restype = C.c_int
+    lib.gmr_retarget_batch_f64_ex.argtypes = [vp, f32p, f32p, f32p, C.c_int32, C.c_int32, f64p, f64p, i32p, f64p, f64p,
+                                              C.POINTER(GmrBatchExtra), C.c_uint32, vp]
+    lib.gmr_retarget_batch_f64_ex.restype = C.c_int
     lib.gmr_retarget_batch_host.argtypes = [vp, f32p, f32p, f32p, C.c_int32, C.c_int32, f32p, f32p, i32p, f32p,
                                             C.c_uint32]
     lib.gmr_retarget_batch_host.restype = C.c_int
+    lib.gmr_retarget_batch_host_ex.argtypes = [vp, f32p, f32p, f32p, C.c_int32, C.c_int32, f32p, f32p, i32p, f32p, i32p,
+                                               C.c_uint32]
+    lib.gmr_retarget_batch_host_ex.restype = C.c_int
     lib.gmr_retarget_batch_ex.argtypes = [vp, f32p, f32p, f32p, C.c_int32, C.c_int32, f32p, f32p, i32p, f32p, f32p,
                                           C.POINTER(GmrBatchExtra), C.c_uint32, vp]
     lib.gmr_retarget_batch_ex.restype = C.c_int
@@ -168,8 +184,8 @@ def load_library() -> C.CDLL:
 
 EXPORTED_SYMBOLS = [
     "gmr_model_create", "gmr_model_destroy", "gmr_retarget_batch", "gmr_retarget_batch_f64",
-    "gmr_retarget_batch_host", "gmr_launch_count", "gmr_last_error", "gmr_kernel_info",
-    "gmr_retarget_batch_ex", "gmr_finalize_motion",
+    "gmr_retarget_batch_host", "gmr_retarget_batch_host_ex", "gmr_launch_count", "gmr_last_error", "gmr_kernel_info",
+    "gmr_retarget_batch_ex", "gmr_retarget_batch_f64_ex", "gmr_finalize_motion",
     "gmr_stream_create", "gmr_stream_destroy", "gmr_stream_reset", "gmr_stream_retarget",
     "gmr_produce_bvh_frames", "gmr_produce_smplx_frames", "gmr_retarget_multi",
 ]

@@ -17,7 +17,7 @@ struct GmrConsts {
   int32_t nb, nh, nhum, nt, nlevel, nq, nv, hroot;
   int32_t use1, use2, max_iter, _pad0;
   uint32_t in1_mask, in2_mask, limited_mask, foot_mask;
-  R damping, lm, gain, tol, dt, _pad1[3];
+  R damping, lm, gain, tol, dt, lie, _pad1[2];
   int16_t parent[GMR_MAX_BODY];       // body -> parent body (-1 root)
   int16_t bhinge[GMR_MAX_BODY];       // body -> hinge index or -1
   int16_t lvl_body[GMR_MAX_BODY];     // bodies sorted by tree depth
@@ -66,7 +66,9 @@ struct GmrDims {
   int32_t o_tg, o_in, o_xp, o_xq, o_u, warp_elems;
   int32_t o_y, rs;            // published factor row of a hinge: slots [0, o_y), then y, 1/d, 2 pad; stride rs
 };
-template <typename R> struct GmrScal { R damping, lm, gain, tol, dt, inv_dt; };
+// `lie`: the reference's small-angle threshold (GmrModelDesc.lie_eps), the same float64-derived value in both precisions:
+// the branch decisions (Taylor vs closed form, the jlog = I shortcut) must follow the float64 reference, not the kernel's dtype
+template <typename R> struct GmrScal { R damping, lm, gain, tol, dt, inv_dt, lie, _pad; };
 
 template <typename R> inline GmrDims gmr_dims_of(const GmrConsts<R>& c) {
   GmrDims d;
@@ -78,7 +80,7 @@ template <typename R> inline GmrDims gmr_dims_of(const GmrConsts<R>& c) {
   return d;
 }
 template <typename R> inline GmrScal<R> gmr_scal_of(const GmrConsts<R>& c) {
-  GmrScal<R> s; s.damping = c.damping; s.lm = c.lm; s.gain = c.gain; s.tol = c.tol; s.dt = c.dt; s.inv_dt = R(1) / c.dt; return s;
+  GmrScal<R> s; s.damping = c.damping; s.lm = c.lm; s.gain = c.gain; s.tol = c.tol; s.dt = c.dt; s.inv_dt = R(1) / c.dt; s.lie = c.lie; s._pad = R(0); return s;
 }
 
 // Validates `d` and fills `c`.  Returns GMR_OK or a negative GMR_E* code; `why` (may be null)
@@ -106,6 +108,7 @@ inline int gmr_fill_consts(const GmrModelDesc* d, GmrConsts<R>* c, const char** 
   m.nq = 7 + d->nhinge; m.nv = 6 + d->nhinge; m.hroot = d->human_root;
   m.use1 = d->use_stage1 != 0; m.use2 = d->use_stage2 != 0; m.max_iter = d->max_iter;
   m.damping = R(d->damping); m.lm = R(d->lm_damping); m.gain = R(d->limit_gain); m.tol = R(d->tol); m.dt = R(d->timestep);
+  m.lie = R(d->lie_eps > 0 ? d->lie_eps : 1e-10);
 
   int depth[GMR_MAX_BODY];
   int maxdepth = 0;

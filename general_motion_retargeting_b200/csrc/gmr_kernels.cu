@@ -483,29 +483,18 @@ int gmr_model_destroy(GmrModel* m) {
   return GMR_OK;
 }
 
-int gmr_retarget_batch(GmrModel* m, const float* pos, const float* quat, const float* ratio, int32_t C, int32_t T,
-                       const float* qpos_init, float* qpos_out, int32_t* iters_out, float* err_out, float* targets_out,
-                       uint32_t flags, void* cuda_stream) {
+static int check_batch_args(GmrModel* m, const void* pos, const void* quat, const void* qpos_out, int32_t C, int32_t T) {
   if (!m) return set_err(GMR_EINVAL, "model is null");
   if (C < 0 || T < 0) return set_err(GMR_EINVAL, "negative batch size");
   if ((C > 0 && T > 0) && (!pos || !quat || !qpos_out)) return set_err(GMR_EINVAL, "pos, quat and qpos_out are required");
   if ((reinterpret_cast<uintptr_t>(quat) & 15u) != 0) return set_err(GMR_EINVAL, "quat must be 16-byte aligned");
-  DeviceGuard g(m->device);
-  if (!g.ok) return set_err(GMR_ECUDA, "cannot select the model's device");
-  if (flags & GMR_FLAG_COMPUTE_F64)
-    return launch<double, float, MAXW_F64>(m, m->d_f64, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out,
-                                           targets_out, flags, (cudaStream_t)cuda_stream);
-  return launch<float, float, MAXW_F32>(m, m->d_f32, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out,
-                                        targets_out, flags, (cudaStream_t)cuda_stream);
+  return GMR_OK;
 }
 
 int gmr_retarget_batch_ex(GmrModel* m, const float* pos, const float* quat, const float* ratio, int32_t C, int32_t T,
                           const float* qpos_init, float* qpos_out, int32_t* iters_out, float* err_out, float* targets_out,
                           const GmrBatchExtra* extra, uint32_t flags, void* cuda_stream) {
-  if (!m) return set_err(GMR_EINVAL, "model is null");
-  if (C < 0 || T < 0) return set_err(GMR_EINVAL, "negative batch size");
-  if ((C > 0 && T > 0) && (!pos || !quat || !qpos_out)) return set_err(GMR_EINVAL, "pos, quat and qpos_out are required");
-  if ((reinterpret_cast<uintptr_t>(quat) & 15u) != 0) return set_err(GMR_EINVAL, "quat must be 16-byte aligned");
+  if (int rc = check_batch_args(m, pos, quat, qpos_out, C, T)) return rc;
   DeviceGuard g(m->device);
   if (!g.ok) return set_err(GMR_ECUDA, "cannot select the model's device");
   if (flags & GMR_FLAG_COMPUTE_F64)
@@ -513,6 +502,28 @@ int gmr_retarget_batch_ex(GmrModel* m, const float* pos, const float* quat, cons
                                            targets_out, flags, (cudaStream_t)cuda_stream, extra);
   return launch<float, float, MAXW_F32>(m, m->d_f32, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out,
                                         targets_out, flags, (cudaStream_t)cuda_stream, extra);
+}
+
+int gmr_retarget_batch(GmrModel* m, const float* pos, const float* quat, const float* ratio, int32_t C, int32_t T,
+                       const float* qpos_init, float* qpos_out, int32_t* iters_out, float* err_out, float* targets_out,
+                       uint32_t flags, void* cuda_stream) {
+  return gmr_retarget_batch_ex(m, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out, targets_out, nullptr, flags, cuda_stream);
+}
+
+int gmr_retarget_batch_f64_ex(GmrModel* m, const float* pos, const float* quat, const float* ratio, int32_t C, int32_t T,
+                              const double* qpos_init, double* qpos_out, int32_t* iters_out, double* err_out,
+                              double* targets_out, const GmrBatchExtra* extra, uint32_t flags, void* cuda_stream) {
+  if (int rc = check_batch_args(m, pos, quat, qpos_out, C, T)) return rc;
+  DeviceGuard g(m->device);
+  if (!g.ok) return set_err(GMR_ECUDA, "cannot select the model's device");
+  return launch<double, double, MAXW_F64>(m, m->d_f64, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out,
+                                          targets_out, flags, (cudaStream_t)cuda_stream, extra);
+}
+
+int gmr_retarget_batch_f64(GmrModel* m, const float* pos, const float* quat, const float* ratio, int32_t C, int32_t T,
+                           const double* qpos_init, double* qpos_out, int32_t* iters_out, double* err_out,
+                           double* targets_out, uint32_t flags, void* cuda_stream) {
+  return gmr_retarget_batch_f64_ex(m, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out, targets_out, nullptr, flags, cuda_stream);
 }
 
 int gmr_finalize_motion(GmrModel* m, const float* qpos, const float* lowest_z, const int32_t* lengths, int32_t C, int32_t T,
@@ -767,23 +778,16 @@ int gmr_stream_retarget(GmrStream* s, const float* pos, const float* quat, uint3
   return GMR_OK;
 }
 
-int gmr_retarget_batch_f64(GmrModel* m, const float* pos, const float* quat, const float* ratio, int32_t C, int32_t T,
-                           const double* qpos_init, double* qpos_out, int32_t* iters_out, double* err_out,
-                           double* targets_out, uint32_t flags, void* cuda_stream) {
-  if (!m) return set_err(GMR_EINVAL, "model is null");
-  if (C < 0 || T < 0) return set_err(GMR_EINVAL, "negative batch size");
-  if ((C > 0 && T > 0) && (!pos || !quat || !qpos_out)) return set_err(GMR_EINVAL, "pos, quat and qpos_out are required");
-  if ((reinterpret_cast<uintptr_t>(quat) & 15u) != 0) return set_err(GMR_EINVAL, "quat must be 16-byte aligned");
-  DeviceGuard g(m->device);
-  if (!g.ok) return set_err(GMR_ECUDA, "cannot select the model's device");
-  return launch<double, double, MAXW_F64>(m, m->d_f64, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out,
-                                          targets_out, flags, (cudaStream_t)cuda_stream);
-}
-
 // Host-buffer entry: clips are cut into chunks; chunk i+1's host->device copy and chunk i-1's
 // device->host copy overlap chunk i's solve on two streams with private staging buffers.
 int gmr_retarget_batch_host(GmrModel* m, const float* pos, const float* quat, const float* ratio, int32_t C, int32_t T,
                             const float* qpos_init, float* qpos_out, int32_t* iters_out, float* err_out, uint32_t flags) {
+  return gmr_retarget_batch_host_ex(m, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out, nullptr, flags);
+}
+
+int gmr_retarget_batch_host_ex(GmrModel* m, const float* pos, const float* quat, const float* ratio, int32_t C, int32_t T,
+                               const float* qpos_init, float* qpos_out, int32_t* iters_out, float* err_out,
+                               int32_t* status_out, uint32_t flags) {
   if (!m) return set_err(GMR_EINVAL, "model is null");
   if (C < 0 || T < 0) return set_err(GMR_EINVAL, "negative batch size");
   if (C == 0 || T == 0) return GMR_OK;
@@ -795,8 +799,8 @@ int gmr_retarget_batch_host(GmrModel* m, const float* pos, const float* quat, co
   // per-clip device bytes (each array padded to 16 bytes per chunk below)
   const size_t b_pos = (size_t)T * nh * 3 * 4, b_quat = (size_t)T * nh * 4 * 4, b_q = (size_t)T * nq * 4,
                b_it = iters_out ? (size_t)T * 2 * 4 : 0, b_err = err_out ? (size_t)T * 2 * 4 : 0,
-               b_ratio = ratio ? 4 : 0, b_init = qpos_init ? (size_t)nq * 4 : 0;
-  const size_t per_clip = b_pos + b_quat + b_q + b_it + b_err + b_ratio + b_init;
+               b_ratio = ratio ? 4 : 0, b_init = qpos_init ? (size_t)nq * 4 : 0, b_st = status_out ? 4 : 0;
+  const size_t per_clip = b_pos + b_quat + b_q + b_it + b_err + b_ratio + b_init + b_st;
   // chunks of whole "waves" (one clip per resident warp) so that every chunk fills the GPU
   const int wave = m->num_sms * ((flags & GMR_FLAG_COMPUTE_F64) ? pick_wpc<double>(m, C) : pick_wpc<float>(m, C));
   int chunk = C;
@@ -811,7 +815,7 @@ int gmr_retarget_batch_host(GmrModel* m, const float* pos, const float* quat, co
     auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t o_pos = 0, o_quat = o_pos + pad(b_pos * n), o_q = o_quat + pad(b_quat * n), o_it = o_q + pad(b_q * n),
                  o_err = o_it + pad(b_it * n), o_ratio = o_err + pad(b_err * n), o_init = o_ratio + pad(b_ratio * n),
-                 total = o_init + pad(b_init * n);
+                 o_st = o_init + pad(b_init * n), total = o_st + pad(b_st * n);
     cudaStream_t st = m->hs[k];
     CK(cudaStreamSynchronize(st));                           // staging buffer k is free again
     if (m->hbuf_bytes[k] < total) {
@@ -825,19 +829,22 @@ int gmr_retarget_batch_host(GmrModel* m, const float* pos, const float* quat, co
     CK(cudaMemcpyAsync(d + o_quat, quat + (size_t)c0 * T * nh * 4, b_quat * n, cudaMemcpyHostToDevice, st));
     if (ratio) CK(cudaMemcpyAsync(d + o_ratio, ratio + c0, b_ratio * n, cudaMemcpyHostToDevice, st));
     if (qpos_init) CK(cudaMemcpyAsync(d + o_init, qpos_init + (size_t)c0 * nq, b_init * n, cudaMemcpyHostToDevice, st));
+    GmrBatchExtra ex{};
+    if (status_out) { ex.status = (int32_t*)(d + o_st); CK(cudaMemsetAsync(d + o_st, 0, b_st * n, st)); }
     if (flags & GMR_FLAG_COMPUTE_F64)
       rc = launch<double, float, MAXW_F64>(m, m->d_f64, (const float*)(d + o_pos), (const float*)(d + o_quat),
                                            ratio ? (const float*)(d + o_ratio) : nullptr, n, T,
                                            qpos_init ? (const float*)(d + o_init) : nullptr, (float*)(d + o_q),
                                            iters_out ? (int32_t*)(d + o_it) : nullptr, err_out ? (float*)(d + o_err) : nullptr,
-                                           nullptr, flags, st);
+                                           nullptr, flags, st, &ex);
     else
       rc = launch<float, float, MAXW_F32>(m, m->d_f32, (const float*)(d + o_pos), (const float*)(d + o_quat),
                                           ratio ? (const float*)(d + o_ratio) : nullptr, n, T,
                                           qpos_init ? (const float*)(d + o_init) : nullptr, (float*)(d + o_q),
                                           iters_out ? (int32_t*)(d + o_it) : nullptr, err_out ? (float*)(d + o_err) : nullptr,
-                                          nullptr, flags, st);
+                                          nullptr, flags, st, &ex);
     if (rc != GMR_OK) break;
+    if (status_out) CK(cudaMemcpyAsync(status_out + c0, d + o_st, b_st * n, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(qpos_out + (size_t)c0 * T * nq, d + o_q, b_q * n, cudaMemcpyDeviceToHost, st));
     if (iters_out) CK(cudaMemcpyAsync(iters_out + (size_t)c0 * T * 2, d + o_it, b_it * n, cudaMemcpyDeviceToHost, st));
     if (err_out) CK(cudaMemcpyAsync(err_out + (size_t)c0 * T * 2, d + o_err, b_err * n, cudaMemcpyDeviceToHost, st));

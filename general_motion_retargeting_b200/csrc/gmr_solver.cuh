@@ -128,11 +128,10 @@ template <typename R> inline void gmr_dims_layout(GmrDims& d) {
   d.warp_elems = gmr_warp_elems<R>(d.nb, d.nh, d.nhum, d.nt, d.maxd);
 }
 
+// relative tolerance of the KKT multiplier sign test (the Lie threshold is a model parameter: GmrScal::lie)
 template <typename R> struct GmrEps;
-// `lie` is the reference's float64 threshold (mink get_epsilon(float64) = 10 eps) in BOTH precisions: the branch
-// decisions (Taylor vs closed form, the jlog = I shortcut) must follow the float64 reference, not the kernel's dtype.
-template <> struct GmrEps<float>  { static constexpr float  lie = 2.220446049250313e-15f; static constexpr float  lam = 1e-5f;  };
-template <> struct GmrEps<double> { static constexpr double lie = 2.220446049250313e-15; static constexpr double lam = 1e-12; };
+template <> struct GmrEps<float>  { static constexpr float  lam = 1e-5f;  };
+template <> struct GmrEps<double> { static constexpr double lam = 1e-12; };
 
 // per-lane registers that persist across lane blocks (what the factorisation keeps live;
 // colder per-lane state sits in the lane-private shared-memory slots GS_LP)
@@ -369,6 +368,7 @@ struct WarpSolver {
   int sr_, sc_;                // this lane's entry of the base block (row slot, column slot)
 #endif
   int stat_refactor;           // factorisations done (uniform)
+  uint32_t stat_flags;         // GMR_STATUS_* events of the current clip (uniform)
   bool convoy;                 // CTA-wide rendezvous before every factorisation (see convoy_arrive)
   volatile int* cta_active;    // shared count of warps that still have clips (convoy mode)
   // working set carried from the previous solve of the same STAGE (uniform).  Four scalars, selected by
@@ -381,7 +381,7 @@ struct WarpSolver {
   // smem_byte_off: offset of this warp's state block from the start of the dynamic shared window
   GMR_FN WarpSolver(const GmrConsts<R>& m, const GmrDims& d, const GmrScal<R>& k, uint32_t smem_byte_off, int lane)
 #endif
-                     : mc(m), dm(d), ks(k), stat_refactor(0), convoy(false), cta_active(nullptr), warm_lo0(0), warm_hi0(0), warm_lo1(0), warm_hi1(0) {
+                     : mc(m), dm(d), ks(k), stat_refactor(0), stat_flags(0), convoy(false), cta_active(nullptr), warm_lo0(0), warm_hi0(0), warm_lo1(0), warm_hi1(0) {
 #ifndef GMR_EMULATE
     lane_ = lane;
     dep_ = lane < d.nh ? (int)m.hdepth[lane] : 0;
@@ -479,11 +479,15 @@ struct WarpSolver {
   // ------------------------------------------------------------------ targets (A1-A5) ------
   // Raw keypoints of one frame (staged in s_in[h] = pos(3) pad quat(4), float) ->
   // scaled + offset targets in s_tg[h] = (pos[3], pad, quat[4]).
-  GMR_FN void update_targets(R ratio, bool to_ground) {
+  // Returns false (uniform) when a keypoint is not finite or a quaternion has no direction: the reference would raise
+  // inside scipy / mink on such a frame (and its dataset script would skip the file); the caller stops the clip.
+  GMR_FN bool update_targets(R ratio, bool to_ground) {
+    bool ok = true;
     GMR_LANES
       if (lane == dm.hroot) { const float* in = s_in() + 8 * lane; s_red()[0] = R(in[0]); s_red()[1] = R(in[1]); s_red()[2] = R(in[2]); }
     GMR_END
     GMR_LANES
+      bool fin = true;
       if (lane < dm.nhum) {
         const R rx = s_red()[0], ry = s_red()[1], rz = s_red()[2];
         const float* in = s_in() + 8 * lane;
@@ -495,7 +499,10 @@ struct WarpSolver {
           p[0] = (R(in[0]) - rx) * s + sr * rx; p[1] = (R(in[1]) - ry) * s + sr * ry; p[2] = (R(in[2]) - rz) * s + sr * rz;
         }
         R q[4] = {R(in[4]), R(in[5]), R(in[6]), R(in[7])};
-        R n = R(1) / g_sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        const R qn2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+        // NaN fails every comparison; float32 inputs cannot overflow R here
+        fin = qn2 > R(1e-30) && qn2 < R(INFINITY) && (g_abs(p[0]) + g_abs(p[1]) + g_abs(p[2])) < R(INFINITY);
+        R n = R(1) / g_sqrt(qn2);
         q[0] *= n; q[1] *= n; q[2] *= n; q[3] *= n;
         R u[4]; q_mul(q, mc.hroff + 4 * lane, u);
         n = R(1) / g_sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2] + u[3] * u[3]);
@@ -505,6 +512,11 @@ struct WarpSolver {
         o[0] = p[0] + g[0]; o[1] = p[1] + g[1]; o[2] = p[2] + g[2]; o[3] = R(0);
         o[4] = u[0]; o[5] = u[1]; o[6] = u[2]; o[7] = u[3];
       }
+#ifdef GMR_EMULATE
+      if (!fin) ok = false;
+#else
+      ok = __all_sync(0xffffffffu, fin);
+#endif
     GMR_END
     if (to_ground) {      // offset_human_data_to_ground, motion_retarget.py:252-270
       R lowest = R(INFINITY);
@@ -514,6 +526,7 @@ struct WarpSolver {
         if (lane < dm.nhum) s_tg()[8 * lane + 2] = s_tg()[8 * lane + 2] - lowest + R(0.1);
       GMR_END
     }
+    return ok;
   }
 
   // ------------------------------------------------------------------ tasks (A7, A9, A10) ---
@@ -544,13 +557,13 @@ struct WarpSolver {
         // SO(3) log
         const R nsq = qe[1] * qe[1] + qe[2] * qe[2] + qe[3] * qe[3];
         R fac;
-        if (nsq < GmrEps<R>::lie) fac = R(2) / qe[0] - R(2) / R(3) * nsq / (qe[0] * qe[0] * qe[0]);
+        if (nsq < ks.lie) fac = R(2) / qe[0] - R(2) / R(3) * nsq / (qe[0] * qe[0] * qe[0]);
         else { const R n = g_sqrt_pos(nsq); fac = R(2) * g_atan2(n, qe[0]) / n; }
         R om[3] = {fac * qe[1], fac * qe[2], fac * qe[3]};
         const R th2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
         // Jinv = I - S/2 + cV S^2, cV = (1 - (theta/2) cot(theta/2)) / theta^2 (also V^-1 of SE3.log)
         R cV;
-        if (th2 < GmrEps<R>::lie) cV = R(1) / R(12);
+        if (th2 < ks.lie) cV = R(1) / R(12);
         else if (th2 < R(0.0625)) cV = R(1) / R(12) + th2 * (R(1) / R(720) + th2 * (R(1) / R(30240) + th2 * R(1.0 / 1209600.0)));   // series: the closed form cancels badly for small theta
         else cV = (R(1) - R(0.5) * g_sqrt_pos(th2) * qe[0] / g_sqrt_pos(nsq)) / th2;
         // rho = Jinv tb = tb - (omega x tb) / 2 + cV omega x (omega x tb)
@@ -578,7 +591,7 @@ struct WarpSolver {
         {
           // Bq, Cq, Dq: Barfoot's Q coefficients
           R Bq, Cq, Dq;
-          if (th2 < GmrEps<R>::lie) {
+          if (th2 < ks.lie) {
             Bq = R(1) / R(6); Cq = -R(1) / R(24); Dq = R(1) / R(120);
           } else if (th2 < R(0.0625)) {                    // series: the closed forms cancel badly for small theta
             Bq = R(1) / R(6) - th2 * (R(1) / R(120) - th2 * (R(1) / R(5040) - th2 * R(1.0 / 362880.0)));
@@ -612,7 +625,7 @@ struct WarpSolver {
               }
             }
           }
-          if (th2 < GmrEps<R>::lie) {
+          if (th2 < ks.lie) {
             // mink's SE3 Jacobian shortcut: for theta^2 < eps, jlog(T) is taken to be the 6x6 identity
             // (the rho-dependent block Q = [rho]x / 2 is dropped).  Reproduced for parity.
             GMR_UNROLL
@@ -1027,7 +1040,8 @@ struct WarpSolver {
     int nchecks = 0;
     bool check = false;
     const int max_as = 8 * dm.nh + 16;
-    for (int it = 0; it < max_as; it++) {
+    int it = 0;
+    for (; it < max_as; it++) {
       const uint32_t pinned = pin_lo | pin_hi;
       if (!check && pinned) {
         GMR_LANES
@@ -1129,7 +1143,8 @@ struct WarpSolver {
       GMR_END
       // release: the first two checks of a solve drop EVERY bound with a multiplier of the wrong sign (a
       // stage switch typically flips several at once), later ones only the worst (the textbook rule, which
-      // cannot cycle).  Whatever the path, the loop only ends on a point that passes this KKT check.
+      // cannot cycle).  The loop ends on a point that passes this KKT check, or - never observed, but not excluded for
+      // the multi-release rule in floating point - on its iteration cap, which the clip's status then reports.
       R lmin = R(0), gmax = R(1); int worst = -1;
       uint32_t drop_all = 0;
 #ifdef GMR_EMULATE
@@ -1164,6 +1179,7 @@ struct WarpSolver {
       pin_lo &= ~drop; pin_hi &= ~drop;
       check = false;
     }
+    if (it >= max_as) stat_flags |= GMR_STATUS_AS_CAP;            // feasible point, optimality not proven
     if (stage == 0) { warm_lo0 = pin_lo; warm_hi0 = pin_hi; } else { warm_lo1 = pin_lo; warm_hi1 = pin_hi; }
     // publish the final step (hinge part) for integration
     GMR_LANES
@@ -1293,8 +1309,11 @@ struct WarpSolver {
     if (io.t_end > 0 && io.t_end < T) T = io.t_end;
     if (tb >= T) return;                                              // nothing of this clip in this launch's frame range
     const bool resume = tb > 0 && io.state;
+    stat_flags = 0;
+    int stat_frame = -1;                                              // frame of the first status event
     {
     const double* const st = io.state ? io.state + (size_t)c * gmr_state_stride(dm.nq) : nullptr;   // not kept live: re-derived at the end
+    if (resume && !(st[dm.nq + 1] == st[dm.nq + 1])) return;          // the clip was stopped in an earlier launch (error = NaN)
     if (resume) set_qpos(st);
     else if (io.qinit) set_qpos(io.qinit + (size_t)c * dm.nq);
     else set_qpos(mc.qpos0);
@@ -1318,7 +1337,10 @@ struct WarpSolver {
     for (;;) {
       if (frame_start) {
         frame_wait();
-        update_targets(s_piv()[0], (flags & GMR_FLAG_OFFSET_TO_GROUND) != 0);
+        if (!update_targets(s_piv()[0], (flags & GMR_FLAG_OFFSET_TO_GROUND) != 0)) {
+          stat_flags |= GMR_STATUS_BAD_INPUT; stat_frame = t;
+          break;                                                       // nothing in flight: the next frame is not staged yet
+        }
         if (t + 1 < T) stage_frame(pos + (size_t)(t + 1) * dm.nhum * 3, quat + (size_t)(t + 1) * dm.nhum * 4);
         stage = first_stage; nsolve = 0; n0 = n1 = 0; e0 = e1 = R(0);
         frame_start = false; need_err = true;
@@ -1352,9 +1374,16 @@ struct WarpSolver {
       }
       if (done) {
         const size_t f = (size_t)c * io.T + t;
+        bool finite = true;
         GMR_LANES
           IO* qo = io.qout + f * dm.nq;
-          for (int i = lane; i < dm.nq; i += 32) qo[i] = IO(s_q()[i]);
+          bool fin = true;
+          for (int i = lane; i < dm.nq; i += 32) { const R v = s_q()[i]; qo[i] = IO(v); fin = fin && (g_abs(v) < R(INFINITY)); }
+#ifdef GMR_EMULATE
+          if (!fin) finite = false;
+#else
+          finite = __all_sync(0xffffffffu, fin);
+#endif
           if (lane == 0) {
             if (io.iters) { io.iters[2 * f] = n0; io.iters[2 * f + 1] = n1; }
             if (io.err) { io.err[2 * f] = IO(e0); io.err[2 * f + 1] = IO(e1); }
@@ -1395,10 +1424,25 @@ struct WarpSolver {
             if (lane == 0 && zm < low) s_piv()[3] = zm;
           GMR_END
         }
+        if (stat_flags && stat_frame < 0) stat_frame = t;
+        if (!finite) {                                                 // the reference's `assert dq is not None`
+          stat_flags |= GMR_STATUS_NONFINITE;
+          frame_wait();                                                // drain the prefetch of frame t + 1
+          break;
+        }
         t++;
         if (t == T) break;
         frame_start = true;
       }
+    }
+    const bool stopped = (stat_flags & GMR_STATUS_FATAL) != 0;
+    if (io.ex.status && stat_flags) {
+      GMR_LANES
+        if (lane == 0) {
+          const int32_t old = io.ex.status[c];
+          io.ex.status[c] = old ? (old | (int32_t)stat_flags) : (int32_t)(stat_flags | ((uint32_t)stat_frame << 8));
+        }
+      GMR_END
     }
     if (io.state) {                                                   // hand-over to the launch that continues this clip
       double* const st = io.state + (size_t)c * gmr_state_stride(dm.nq);
@@ -1406,7 +1450,7 @@ struct WarpSolver {
         for (int i = lane; i < dm.nq; i += 32) st[i] = (double)s_q()[i];
         if (lane == 0) {
           st[dm.nq] = (double)s_piv()[3];
-          st[dm.nq + 1] = (double)(dm.use2 ? e1 : e0);
+          st[dm.nq + 1] = stopped ? (double)NAN : (double)(dm.use2 ? e1 : e0);
           uint32_t* w = reinterpret_cast<uint32_t*>(st + dm.nq + 2);
           w[0] = warm_lo0; w[1] = warm_hi0; w[2] = warm_lo1; w[3] = warm_hi1;
         }

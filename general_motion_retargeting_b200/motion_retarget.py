@@ -39,6 +39,24 @@ def _is_torch(x) -> bool:
     return type(x).__module__.split(".")[0] == "torch"
 
 
+class RetargetFailure(RuntimeError):
+    """Raised by the batched entries when the kernel reports a fatal per-clip status: what the reference signals per
+    clip with an exception out of `retarget()` (scipy / mink on non-finite targets, `assert dq is not None` in
+    mink.solve_ik — motion_retarget.py:147-150), which scripts/smplx_to_robot_dataset.py:62-76,96-100 catches per
+    file.  `clip_ids` / `frames` / `status` name the clips, `result` holds what the call would have returned (every
+    other clip is valid; a failed clip's frames from `frames[i]` on are not written)."""
+
+    def __init__(self, clip_ids, frames, status, result=None):
+        self.clip_ids, self.frames, self.status, self.result = list(clip_ids), list(frames), status, result
+        what = ", ".join(f"clip {c} at frame {f}" for c, f in list(zip(self.clip_ids, self.frames))[:8])
+        more = "" if len(self.clip_ids) <= 8 else f" (+{len(self.clip_ids) - 8} more)"
+        super().__init__(f"retargeting failed for {len(self.clip_ids)} clip(s): non-finite keypoints / zero-norm "
+                         f"quaternion or no QP solution: {what}{more}")
+
+
+_SOLVERS = ("daqp", "quadprog", "proxqp", "osqp", "cvxopt", "ecos", "scs", "clarabel", "highs", "piqp", "qpalm")
+
+
 class _Handle:
     """One gmr_model_create() handle per (instance, device)."""
 
@@ -89,13 +107,21 @@ class GeneralMotionRetargeting:
         device: Union[int, str, None] = None,
         precision: str = "f64",
     ) -> None:
-        # the robot model and IK config (KeyError on unknown names, like the reference's dict lookups)
+        # the robot model and IK config (KeyError on unknown names, like the reference's dict lookups).  xml_file is the
+        # MJCF path callers hand to KinematicsModel (smplx_to_robot_dataset.py:94); the model itself comes from the
+        # compiled pack, which load_pack() has checked against that very file when a checkout is present.
         self.xml_file = str(ROBOT_XML_DICT[tgt_robot])
         self._robot, cfg, _pack = load_pack(src_human, tgt_robot)
+        self.model_source = str(_pack.get("loaded_from", ""))
         self._cfg: IKConfig = cfg
         if verbose:
             print("Use robot model: ", self.xml_file)
             print("Use IK config: ", IK_CONFIG_DICT[src_human][tgt_robot])
+            print("Loaded from: ", self.model_source, "(source sha256", str(_pack.get("source_sha256", "?"))[:12] + ")")
+        if solver not in _SOLVERS:
+            # the reference hands `solver` to qpsolvers, which raises for a name it does not know; every supported
+            # solver returns the same unique minimiser of the strictly convex QP, computed here exactly on the GPU
+            raise ValueError(f"unknown QP solver '{solver}' (qpsolvers names: {', '.join(_SOLVERS)})")
         if precision not in ("f32", "f64"):
             raise ValueError("precision must be 'f32' or 'f64'")
         self.precision = precision
@@ -117,7 +143,7 @@ class GeneralMotionRetargeting:
         self.use_ik_match_table2 = cfg.use_ik_match_table2
         self.ground = cfg.ground_height * np.array([0, 0, 1])
         self.max_iter = 10
-        self.solver = solver          # kept for signature parity; the QP is solved exactly on the GPU
+        self.solver = solver          # validated above; the QP's unique minimiser is computed exactly on the GPU
         self.damping = damping
 
         self._table: TaskTable = compile_task_table(self._robot, cfg)
@@ -331,8 +357,30 @@ class GeneralMotionRetargeting:
                 quat[ci, len(clip):] = quat[ci, len(clip) - 1]
         return pos, quat, lengths
 
+    def _check_batch_shapes(self, pos, quat, heights, qpos_init, lengths=None):
+        """ValueError for anything the kernel would otherwise read out of bounds (the C ABI takes raw pointers)."""
+        nq, nh = self._robot.nq, self._table.nh
+        if len(pos.shape) != 4 or len(quat.shape) != 4 or tuple(pos.shape[2:]) != (nh, 3) or tuple(quat.shape[2:]) != (nh, 4) \
+                or tuple(pos.shape[:2]) != tuple(quat.shape[:2]):
+            raise ValueError(f"expected pos [C,T,{nh},3] and quat [C,T,{nh},4], got {tuple(pos.shape)} and {tuple(quat.shape)}")
+        Cn = int(pos.shape[0])
+        if heights is not None and tuple(np.shape(heights)) != (Cn,):
+            raise ValueError(f"heights must have shape ({Cn},), got {tuple(np.shape(heights))}")
+        if qpos_init is not None and tuple(np.shape(qpos_init)) != (Cn, nq):
+            raise ValueError(f"qpos_init must have shape ({Cn}, {nq}), got {tuple(np.shape(qpos_init))}")
+        if lengths is not None and tuple(np.shape(lengths)) != (Cn,):
+            raise ValueError(f"lengths must have shape ({Cn},), got {tuple(np.shape(lengths))}")
+        return Cn, int(pos.shape[1])
+
+    @staticmethod
+    def _raise_on_status(status: np.ndarray, result, on_error: str):
+        """status [C] int32 (GMR_STATUS_* | frame << 8) -> RetargetFailure for the fatal bits."""
+        bad = np.nonzero(status & _native.GMR_STATUS_FATAL)[0]
+        if on_error == "raise" and bad.size:
+            raise RetargetFailure(bad.tolist(), (status[bad] >> 8).tolist(), status, result)
+
     def retarget_batch(self, pos, quat=None, heights=None, qpos_init=None, offset_to_ground: bool = False,
-                       return_info: bool = False, precision: Optional[str] = None, out=None):
+                       return_info: bool = False, precision: Optional[str] = None, out=None, on_error: str = "raise"):
         """Retarget C clips of T frames.
 
         pos [C,T,nh,3] metres world Z-up, quat [C,T,nh,4] wxyz, bodies ordered as
@@ -341,9 +389,14 @@ class GeneralMotionRetargeting:
         (no host copies) and a torch tensor is returned; numpy arrays go through the library's
         host-buffer pipeline and numpy is returned.  A list of reference-format clips is packed
         first.  `out` (host path): preallocated float32 [C,T,nq] array, e.g. pinned memory.
-        `precision`: arithmetic of the kernel, "f64" (default: matches the float64 reference to
-        rounding) or "f32" (~1.6x faster; same answer to ~1e-6 rad except that the reference's
-        `error decrease > 1e-3` loop exit flips on ~2e-4 of the frames).
+        `precision`: arithmetic of the kernel, "f64" (default: the reference's own precision) or
+        "f32" (APPROXIMATE: ~1.3x faster, but outside the 1e-3 rad parity gate on ill-conditioned
+        clips).
+        `on_error`: what to do when a clip fails the way the reference raises (non-finite keypoints,
+        zero-norm quaternion, no QP solution): "raise" (default) raises `RetargetFailure` naming the
+        clips (the result for all other clips is in `.result`; this synchronises the stream),
+        "status" appends the per-clip status words [C] int32 to the return value, "ignore" does
+        neither and stays asynchronous on the torch path.
         Returns qpos [C,T,nq]: torch float64/float32 for CUDA inputs, numpy float32 for host
         inputs; with return_info also (iters [C,T,2] int32, err [C,T,2])."""
         if quat is None:
@@ -351,11 +404,11 @@ class GeneralMotionRetargeting:
         precision = precision or self.precision
         if precision not in ("f32", "f64"):
             raise ValueError("precision must be 'f32' or 'f64'")
+        if on_error not in ("raise", "status", "ignore"):
+            raise ValueError("on_error must be 'raise', 'status' or 'ignore'")
         flags = FLAG_OFFSET_TO_GROUND if offset_to_ground else 0
         nq, nh = self._robot.nq, self._table.nh
-        if tuple(pos.shape[2:]) != (nh, 3) or tuple(quat.shape[2:]) != (nh, 4) or tuple(pos.shape[:2]) != tuple(quat.shape[:2]):
-            raise ValueError(f"expected pos [C,T,{nh},3] and quat [C,T,{nh},4], got {tuple(pos.shape)} and {tuple(quat.shape)}")
-        Cn, T = int(pos.shape[0]), int(pos.shape[1])
+        Cn, T = self._check_batch_shapes(pos, quat, heights, qpos_init)
 
         if _is_torch(pos):
             import torch
@@ -377,13 +430,21 @@ class GeneralMotionRetargeting:
                 d_q = torch.empty((Cn, T, nq), dtype=dt, device=dev)
                 d_it = torch.zeros((Cn, T, 2), dtype=torch.int32, device=dev) if return_info else None
                 d_err = torch.zeros((Cn, T, 2), dtype=dt, device=dev) if return_info else None
-                fn = self._lib.gmr_retarget_batch_f64 if f64 else self._lib.gmr_retarget_batch
+                d_st = torch.zeros((Cn,), dtype=torch.int32, device=dev) if on_error != "ignore" else None
+                ex = _native.GmrBatchExtra(None, None, None, None, None if d_st is None else d_st.data_ptr())
+                fn = self._lib.gmr_retarget_batch_f64_ex if f64 else self._lib.gmr_retarget_batch_ex
                 rc = fn(h.ptr, d_pos.data_ptr(), d_quat.data_ptr(), d_ratio.data_ptr(), Cn, T,
                         None if d_init is None else d_init.data_ptr(), d_q.data_ptr(),
                         None if d_it is None else d_it.data_ptr(), None if d_err is None else d_err.data_ptr(),
-                        None, flags, torch.cuda.current_stream(dev).cuda_stream)
+                        None, C.byref(ex), flags, torch.cuda.current_stream(dev).cuda_stream)
                 self._check(rc, "gmr_retarget_batch")
-            return (d_q, d_it, d_err) if return_info else d_q
+                res = (d_q, d_it, d_err) if return_info else d_q
+                if on_error == "raise":
+                    if bool(d_st.any()):                                  # one 1-byte read-back; synchronises
+                        self._raise_on_status(d_st.cpu().numpy(), res, on_error)
+                elif on_error == "status":
+                    res = (res + (d_st,)) if return_info else (d_q, d_st)
+            return res
 
         # host buffers: float32 in / float32 out, arithmetic in the requested precision
         if precision == "f64":
@@ -404,18 +465,25 @@ class GeneralMotionRetargeting:
             qpos = np.empty((Cn, T, nq), np.float32)
         iters = np.zeros((Cn, T, 2), np.int32) if return_info else None
         err = np.zeros((Cn, T, 2), np.float32) if return_info else None
-        rc = self._lib.gmr_retarget_batch_host(
+        status = np.zeros((Cn,), np.int32) if on_error != "ignore" else None
+        rc = self._lib.gmr_retarget_batch_host_ex(
             h.ptr, a_pos.ctypes.data, a_quat.ctypes.data, a_ratio.ctypes.data, Cn, T,
             None if a_init is None else a_init.ctypes.data, qpos.ctypes.data,
-            None if iters is None else iters.ctypes.data, None if err is None else err.ctypes.data, flags)
+            None if iters is None else iters.ctypes.data, None if err is None else err.ctypes.data,
+            None if status is None else status.ctypes.data, flags)
         self._check(rc, "gmr_retarget_batch_host")
-        return (qpos, iters, err) if return_info else qpos
+        res = (qpos, iters, err) if return_info else qpos
+        if on_error == "raise":
+            self._raise_on_status(status, res, on_error)
+        elif on_error == "status":
+            res = (res + (status,)) if return_info else (qpos, status)
+        return res
 
 
     # ------------------------------------------------------------------ dataset entry ---------
     def retarget_dataset(self, pos, quat=None, heights=None, lengths=None, height_adjust: bool = True,
                          root_origin_offset: bool = True, precision: Optional[str] = None, fps: float = 30.0,
-                         as_numpy: bool = True):
+                         as_numpy: bool = True, on_error: str = "raise"):
         """What `process_file` of scripts/smplx_to_robot_dataset.py:78-146 (and bvh_to_robot_dataset.py:96-157)
         computes for a whole batch of files in two launches: the per-frame IK (as `retarget_batch`) with the
         post-solve forward kinematics fused in (`local_body_pos`, the clip-wide lowest body height), then one
@@ -423,6 +491,8 @@ class GeneralMotionRetargeting:
         `root_rot` (xyzw) and `dof_pos`.  `height_adjust`/`root_origin_offset` are the scripts' HEIGHT_ADJUST and
         ROOT_ORIGIN_OFFSET switches (True/True in the SMPL-X script, False/False in the BVH script).
         `lengths` [C]: frames per clip for ragged batches (padding frames are not solved).
+        `on_error`: "raise" raises `RetargetFailure` for clips the reference would raise on; "skip" mirrors the
+        scripts' per-file try/except (smplx_to_robot_dataset.py:62-76,96-100): a failed clip's entry is None.
         Returns a list of C motion dicts in the reference's pkl layout
         (fps, root_pos [T,3], root_rot [T,4] xyzw, dof_pos [T,ndof], local_body_pos [T,nbody,3], link_body_list)."""
         import torch
@@ -435,9 +505,9 @@ class GeneralMotionRetargeting:
         with torch.cuda.device(dev):
             d_pos = torch.as_tensor(pos).to(dev, torch.float32).contiguous()
             d_quat = torch.as_tensor(quat).to(dev, torch.float32).contiguous()
-            Cn, T = int(d_pos.shape[0]), int(d_pos.shape[1])
-            if tuple(d_pos.shape[2:]) != (nh, 3) or tuple(d_quat.shape) != (Cn, T, nh, 4):
-                raise ValueError(f"expected pos [C,T,{nh},3] and quat [C,T,{nh},4]")
+            Cn, T = self._check_batch_shapes(d_pos, d_quat, heights, None, lengths)
+            if on_error not in ("raise", "skip"):
+                raise ValueError("on_error must be 'raise' or 'skip'")
             if heights is None:
                 d_ratio = torch.full((Cn,), self._ratio, dtype=torch.float32, device=dev)
             else:
@@ -446,7 +516,9 @@ class GeneralMotionRetargeting:
             d_q = torch.zeros((Cn, T, nq), dtype=torch.float32, device=dev)
             d_lbp = torch.zeros((Cn, T, nb, 3), dtype=torch.float32, device=dev)
             d_low = torch.zeros((Cn,), dtype=torch.float32, device=dev)
-            ex = _native.GmrBatchExtra(None if d_len is None else d_len.data_ptr(), d_lbp.data_ptr(), d_low.data_ptr(), None)
+            d_st = torch.zeros((Cn,), dtype=torch.int32, device=dev)
+            ex = _native.GmrBatchExtra(None if d_len is None else d_len.data_ptr(), d_lbp.data_ptr(), d_low.data_ptr(), None,
+                                       d_st.data_ptr())
             st = torch.cuda.current_stream(dev).cuda_stream
             flags = FLAG_COMPUTE_F64 if precision == "f64" else 0
             rc = self._lib.gmr_retarget_batch_ex(h.ptr, d_pos.data_ptr(), d_quat.data_ptr(), d_ratio.data_ptr(), Cn, T, None,
@@ -459,12 +531,17 @@ class GeneralMotionRetargeting:
                                                Cn, T, int(height_adjust), int(root_origin_offset),
                                                d_rp.data_ptr(), d_rr.data_ptr(), d_dof.data_ptr(), st)
             self._check(rc, "gmr_finalize_motion")
+            status = d_st.cpu().numpy()
+            failed = (status & _native.GMR_STATUS_FATAL) != 0
+            if failed.any() and on_error == "raise":
+                self._raise_on_status(status, None, "raise")
             if not as_numpy:
-                return {"fps": fps, "root_pos": d_rp, "root_rot": d_rr, "dof_pos": d_dof, "local_body_pos": d_lbp,
+                return {"status": d_st, "fps": fps, "root_pos": d_rp, "root_rot": d_rr, "dof_pos": d_dof, "local_body_pos": d_lbp,
                         "lowest_z": d_low, "qpos": d_q, "link_body_list": list(self._robot.body_names), "lengths": d_len}
             rp, rr, dof, lbp = (x.cpu().numpy() for x in (d_rp, d_rr, d_dof, d_lbp))
         n = [T] * Cn if lengths is None else [int(x) for x in np.asarray(lengths)]
-        return [{"fps": fps, "root_pos": rp[c, :n[c]], "root_rot": rr[c, :n[c]], "dof_pos": dof[c, :n[c]],
+        return [None if failed[c] else
+                {"fps": fps, "root_pos": rp[c, :n[c]], "root_rot": rr[c, :n[c]], "dof_pos": dof[c, :n[c]],
                  "local_body_pos": lbp[c, :n[c]], "link_body_list": list(self._robot.body_names)} for c in range(Cn)]
 
     @staticmethod
@@ -477,6 +554,8 @@ class GeneralMotionRetargeting:
 
         def one(args):
             m, p = args
+            if m is None:          # a clip skipped by retarget_dataset(on_error="skip")
+                return
             d = os.path.dirname(p)
             if d:
                 os.makedirs(d, exist_ok=True)

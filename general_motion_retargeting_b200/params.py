@@ -12,9 +12,12 @@ with ``compile_pack``; tests check both routes agree.
 """
 from __future__ import annotations
 
+import hashlib
 import json
 import os
 import pathlib
+import re
+import warnings
 from typing import Dict, Optional, Tuple
 
 from .ik_config import IKConfig
@@ -106,6 +109,35 @@ def pack_path(src_human: str, tgt_robot: str) -> pathlib.Path:
     return PACK_ROOT / f"{src_human}_to_{tgt_robot}.json"
 
 
+_INCLUDE_RE = re.compile(rb"<include\s+file\s*=\s*[\"']([^\"']+)[\"']")
+
+
+def source_digest(xml_path: os.PathLike, ik_path: os.PathLike) -> str:
+    """sha256 over the bytes of the MJCF, every file it <include>s (recursively, in order) and the IK JSON:
+    the identity of the SOURCES a pack was compiled from.  `load_pack` compares it with the checkout's files so
+    that an edited offset, weight, scale or joint range is never silently ignored in favour of a stale pack."""
+    h = hashlib.sha256()
+    main_dir = os.path.dirname(os.fspath(xml_path))
+
+    def feed(path, depth=0):
+        with open(path, "rb") as f:
+            data = f.read()
+        h.update(data)
+        if depth < 8:
+            for m in _INCLUDE_RE.finditer(data):
+                name = m.group(1).decode()
+                for cand in (os.path.join(os.path.dirname(path), name), os.path.join(main_dir, name)):
+                    if os.path.isfile(cand):
+                        feed(cand, depth + 1)
+                        break
+
+    feed(os.fspath(xml_path))
+    h.update(b"\0ik\0")
+    with open(ik_path, "rb") as f:
+        h.update(f.read())
+    return h.hexdigest()
+
+
 def compile_pack(src_human: str, tgt_robot: str, root: Optional[os.PathLike] = None) -> dict:
     """Compile the raw MJCF + IK JSON of a reference checkout into a pack dict."""
     rroot = pathlib.Path(root) if root is not None else reference_root()
@@ -121,6 +153,7 @@ def compile_pack(src_human: str, tgt_robot: str, root: Optional[os.PathLike] = N
         "tgt_robot": tgt_robot,
         "xml_rel": xml_rel,
         "ik_config_file": cfg_file,
+        "source_sha256": source_digest(asset_root / xml_rel, ik_root / cfg_file),
         "robot": robot.to_dict(),
         "ik_config": cfg.to_dict(),
     }
@@ -137,10 +170,27 @@ def load_pack(src_human: str, tgt_robot: str) -> Tuple[RobotModel, IKConfig, dic
     key = (src_human, tgt_robot)
     if key not in _PACK_CACHE:
         p = pack_path(src_human, tgt_robot)
+        d = None
         if p.is_file():
             with open(p) as f:
-                _PACK_CACHE[key] = json.load(f)
-        else:
-            _PACK_CACHE[key] = compile_pack(src_human, tgt_robot)
+                d = json.load(f)
+            d["loaded_from"] = str(p)
+            # a checkout next to the pack is the source of truth (ROBOT_XML_DICT / IK_CONFIG_DICT point at ITS files):
+            # if its MJCF / IK JSON differ from what the pack was compiled from, compile the checkout's files instead
+            root = reference_root()
+            if root is not None:
+                asset_root, ik_root = _paths(root)
+                try:
+                    live = source_digest(asset_root / d["xml_rel"], ik_root / d["ik_config_file"])
+                except OSError:
+                    live = None
+                if live is not None and live != d.get("source_sha256"):
+                    warnings.warn(f"model pack {p.name} is stale against {root} (source digest differs): compiling the "
+                                  f"checkout's MJCF / IK config instead; refresh with tools/compile_packs.py", stacklevel=2)
+                    d = None
+        if d is None:
+            d = compile_pack(src_human, tgt_robot)
+            d["loaded_from"] = str(reference_root())
+        _PACK_CACHE[key] = d
     d = _PACK_CACHE[key]
     return RobotModel.from_dict(d["robot"]), IKConfig.from_dict(d["ik_config"]), d

@@ -29,6 +29,17 @@ extern "C" {
 #define GMR_MAX_HUMAN    32
 #define GMR_MAX_TASK     32
 
+/* per-clip status bits (GmrBatchExtra.status / status_out of the host entry).  The reference fails per clip with a
+ * Python exception (mink TargetNotSet / `assert dq is not None` in motion_retarget.py:147-150, caught per file by
+ * scripts/smplx_to_robot_dataset.py:62-76,96-100 which then skips the file); the batched kernel records the same
+ * events per clip instead.  status = bits | (frame of the first event << 8). */
+#define GMR_STATUS_BAD_INPUT   1u  /* non-finite keypoint or zero-norm quaternion: the clip stops at that frame, later
+                                      frames of the clip are NOT written                                            */
+#define GMR_STATUS_AS_CAP      2u  /* the active-set loop of some solve hit its iteration cap: the step taken is
+                                      feasible but was not proven optimal; the clip continues                       */
+#define GMR_STATUS_NONFINITE   4u  /* non-finite configuration after a step (the QP "has no solution"): clip stops   */
+#define GMR_STATUS_FATAL       (GMR_STATUS_BAD_INPUT | GMR_STATUS_NONFINITE)
+
 /* flags for gmr_retarget_batch */
 #define GMR_FLAG_OFFSET_TO_GROUND  1u  /* retarget(..., offset_to_ground=True), motion_retarget.py:122-123,252-270 */
 #define GMR_FLAG_COMPUTE_F64       4u  /* gmr_retarget_batch / _host: float32 buffers, float64 arithmetic in the kernel */
@@ -78,6 +89,10 @@ typedef struct GmrModelDesc {
   double  tol;                   /* loop threshold on the error decrease        */
   double  timestep;              /* model.opt.timestep                          */
   int32_t max_iter;              /* conditional iterations per stage            */
+  double  lie_eps;               /* mink.lie.utils.get_epsilon(float64): threshold of the small-angle branches of
+                                    SO3.log / SE3.log / jlog (Taylor series, the jlog = I shortcut).  mink is not
+                                    vendored in the reference; upstream is recalled as 1e-10, round 1 assumed
+                                    2.2e-15 (10 eps).  0 selects 1e-10.                                          */
 } GmrModelDesc;
 
 typedef struct GmrModel GmrModel;  /* opaque; owns device copies of the tables; immutable after create */
@@ -115,6 +130,8 @@ typedef struct GmrBatchExtra {
   float* lowest_z;            /* [C] min over frames and bodies of the world z (torch.min(body_pos[..., 2])) */
   uint32_t* warm_state;       /* [C,4] in/out: the solver's working sets (joints resting on a limit) carried from
                                  one call to the next when a clip is fed in pieces; zeros to start            */
+  int32_t* status;            /* [C] out: GMR_STATUS_* bits | first event's frame << 8; 0 = clean.  The caller zeroes
+                                 it (bits are OR-ed in, so one array can collect several calls)               */
 } GmrBatchExtra;
 
 /* gmr_retarget_batch with extras; flags may carry GMR_FLAG_COMPUTE_F64. */
@@ -188,12 +205,23 @@ int gmr_retarget_batch_f64(GmrModel* model, const float* pos, const float* quat,
                            int32_t* iters_out, double* err_out, double* targets_out,
                            uint32_t flags, void* cuda_stream);
 
+/* float64-buffer variant with extras (GmrBatchExtra: ragged lengths, FK epilogue, working sets, per-clip status) */
+int gmr_retarget_batch_f64_ex(GmrModel* model, const float* pos, const float* quat, const float* ratio,
+                              int32_t C, int32_t T, const double* qpos_init, double* qpos_out,
+                              int32_t* iters_out, double* err_out, double* targets_out,
+                              const GmrBatchExtra* extra, uint32_t flags, void* cuda_stream);
+
 /* Same call with HOST buffers (pinned or pageable): the library chunks the clips, overlaps
  * H2D copies, the solve and D2H copies on its own streams and returns when qpos_out is
  * complete.  This is what a dataset script calls. */
 int gmr_retarget_batch_host(GmrModel* model, const float* pos, const float* quat, const float* ratio,
                             int32_t C, int32_t T, const float* qpos_init, float* qpos_out,
                             int32_t* iters_out, float* err_out, uint32_t flags);
+
+/* ... with per-clip status words (GMR_STATUS_*; host pointer [C], written by the call, may be NULL) */
+int gmr_retarget_batch_host_ex(GmrModel* model, const float* pos, const float* quat, const float* ratio,
+                               int32_t C, int32_t T, const float* qpos_init, float* qpos_out,
+                               int32_t* iters_out, float* err_out, int32_t* status_out, uint32_t flags);
 
 /* number of kernel launches issued by this library since load (for bench bookkeeping) */
 int64_t gmr_launch_count(void);

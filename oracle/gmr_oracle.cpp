@@ -29,9 +29,12 @@ namespace {
 constexpr int MAXB = GMR_MAX_BODY, MAXH = GMR_MAX_HINGE, MAXV = 6 + GMR_MAX_HINGE,
               MAXT = GMR_MAX_TASK, MAXN = GMR_MAX_HUMAN;
 
-template <typename R> struct Eps;
-template <> struct Eps<double> { static constexpr double v = 2.220446049250313e-16 * 10.0; };
-template <> struct Eps<float> { static constexpr float v = 1.1920929e-07f * 10.0f; };   // mink get_epsilon(dtype)
+// mink.lie.utils.get_epsilon(dtype): the threshold of every small-angle branch of the Lie code.  The value is not
+// stated anywhere in /root/reference (mink is not vendored); upstream mink (jaxlie-derived lie/utils.py) is recalled
+// as 1e-10 for float64 / 1e-5 for float32, round 1 assumed 10 * machine epsilon.  It is therefore a PARAMETER
+// (GmrModelDesc.lie_eps; 0 = 1e-10) and the parity matrix runs with both values (tests/test_lie_eps.py).
+static double g_lie_eps = 1e-10;
+template <typename R> struct Eps { static R v() { return R(g_lie_eps); } };
 
 template <typename R> struct V3 { R x, y, z; };
 template <typename R> struct Q4 { R w, x, y, z; };
@@ -79,7 +82,7 @@ template <typename R> inline void mm3(const R A[9], const R B[9], R C[9]) {
 template <typename R> inline void tr3(const R A[9], R B[9]) { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) B[3 * i + j] = A[3 * j + i]; }
 
 template <typename R> void so3_log(const Q4<R>& q, R out[3]) {                        // mink SO3.log
-  const R eps = Eps<R>::v;
+  const R eps = Eps<R>::v();
   R w = q.w, nsq = q.x * q.x + q.y * q.y + q.z * q.z;
   bool taylor = nsq < eps;
   R ns = taylor ? R(1) : std::sqrt(nsq), ws = taylor ? w : R(1), f;
@@ -91,7 +94,7 @@ template <typename R> void so3_log(const Q4<R>& q, R out[3]) {                  
 }
 
 template <typename R> void se3_log(const Q4<R>& q, const V3<R>& t, R out[6]) {        // mink SE3.log
-  const R eps = Eps<R>::v;
+  const R eps = Eps<R>::v();
   R om[3]; so3_log(q, om);
   R th2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
   R S[9], S2[9]; skew(om, S); mm3(S, S, S2);
@@ -109,7 +112,7 @@ template <typename R> void se3_log(const Q4<R>& q, const V3<R>& t, R out[6]) {  
 static bool g_stable_lie = false;
 
 template <typename R> void so3_ljacinv(const R om[3], R J[9]) {                       // mink SO3.ljacinv
-  const R eps = Eps<R>::v;
+  const R eps = Eps<R>::v();
   R th = std::sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]), A;
   if (th < eps) { R t2 = th * th; A = R(1) / R(12) * (R(1) + t2 / R(60) * (R(1) + t2 / R(42) * (R(1) + t2 / R(40)))); }
   else if (g_stable_lie) { R h = R(0.5) * th; A = (R(1) - h * std::cos(h) / std::sin(h)) / (th * th); }
@@ -119,7 +122,7 @@ template <typename R> void so3_ljacinv(const R om[3], R J[9]) {                 
 }
 
 template <typename R> void se3_ljacinv(const R xi[6], R J[36]) {                      // mink SE3.ljacinv + _getQ
-  const R eps = Eps<R>::v;
+  const R eps = Eps<R>::v();
   const R* rho = xi; const R* om = xi + 3;
   R th2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
   for (int i = 0; i < 36; i++) J[i] = (i % 7 == 0) ? R(1) : R(0);
@@ -463,6 +466,7 @@ extern "C" int gmr_oracle_retarget_batch(const GmrModelDesc* desc, const float* 
   if (!desc || !pos || !quat || !qpos_out || C < 0 || T < 0) return GMR_EINVAL;
   if (desc->nbody > MAXB || desc->nhinge > MAXH || desc->nhuman > MAXN || desc->ntask > MAXT) return GMR_ELIMIT;
   g_stable_lie = (flags & GMR_ORACLE_FLAG_STABLE_LIE) != 0;
+  g_lie_eps = desc->lie_eps > 0 ? desc->lie_eps : 1e-10;
   if (precision_bits == 32)
     return run_batch<float>(desc, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out, flags, nthreads);
   return run_batch<double>(desc, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out, flags, nthreads);

@@ -98,7 +98,19 @@ def skew(v: np.ndarray) -> np.ndarray:
 # --------------------------------------------------------------------------------------
 # Lie-group pieces, following mink/lie/so3.py and mink/lie/se3.py
 # --------------------------------------------------------------------------------------
-_EPS64 = float(np.finfo(np.float64).eps) * 10.0   # mink.lie.utils.get_epsilon(float64)
+# mink.lie.utils.get_epsilon(float64): threshold of every small-angle branch below.  mink is not vendored and
+# /root/reference never states the value; upstream (jaxlie-derived lie/utils.py) is recalled as 1e-10 for float64,
+# round 1 assumed 10 * machine epsilon = 2.2e-15.  It is a module-level PARAMETER so that the parity matrix can be
+# run with both (tests/test_lie_eps.py); the C++ port and the CUDA kernel take the same value through
+# GmrModelDesc.lie_eps.
+LIE_EPS_DEFAULT = 1e-10
+LIE_EPS_ROUND1 = float(np.finfo(np.float64).eps) * 10.0
+_EPS64 = LIE_EPS_DEFAULT
+
+
+def set_lie_eps(eps: float) -> None:
+    global _EPS64
+    _EPS64 = float(eps)
 
 
 def so3_log(q: np.ndarray) -> np.ndarray:

@@ -40,14 +40,14 @@ def load() -> C.CDLL:
 
 
 def retarget_batch(robot, table, pos, quat, ratio=None, qpos_init=None, flags=0, nthreads=0, precision_bits=64,
-                   damping=0.5):
+                   damping=0.5, lie_eps=0.0):
     """pos[C,T,nh,3], quat[C,T,nh,4] float32; ratio[C] float32 or None → (qpos[C,T,nq] f64, iters[C,T,2], err[C,T,2])."""
     lib = load()
     pos = np.ascontiguousarray(pos, np.float32)
     quat = np.ascontiguousarray(quat, np.float32)
     Cn, T = pos.shape[0], pos.shape[1]
     assert pos.shape == (Cn, T, table.nh, 3) and quat.shape == (Cn, T, table.nh, 4)
-    desc, keep = build_desc(robot, table, damping=damping)
+    desc, keep = build_desc(robot, table, damping=damping, lie_eps=lie_eps)
     r = None if ratio is None else np.ascontiguousarray(ratio, np.float32)
     qi = None if qpos_init is None else np.ascontiguousarray(qpos_init, np.float64)
     qpos = np.zeros((Cn, T, robot.nq), np.float64)

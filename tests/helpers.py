@@ -18,14 +18,14 @@ def problem(src, robot):
     return m, compile_task_table(m, cfg), pack
 
 
-def emu_retarget_batch(robot, table, pos, quat, ratio, bits=64, flags=0, qpos_init=None, max_iter=10, nthreads=0):
+def emu_retarget_batch(robot, table, pos, quat, ratio, bits=64, flags=0, qpos_init=None, max_iter=10, nthreads=0, lie_eps=0.0):
     """Lane-serial host build of the kernel body (tests/emu) — a debugging aid, not a product path."""
     global _emu
     if _emu is None:
         _emu = C.CDLL(EMU)
         _emu.gmr_emu_retarget_batch.restype = C.c_int
     Cn, T = pos.shape[:2]
-    desc, keep = build_desc(robot, table, max_iter=max_iter)
+    desc, keep = build_desc(robot, table, max_iter=max_iter, lie_eps=lie_eps)
     qpos = np.zeros((Cn, T, robot.nq)); iters = np.zeros((Cn, T, 2), np.int32); err = np.zeros((Cn, T, 2))
     tg = np.zeros((Cn, T, table.nh, 7)); refac = C.c_int64(0)
     pos = np.ascontiguousarray(pos, np.float32); quat = np.ascontiguousarray(quat, np.float32)
@@ -53,8 +53,10 @@ def compare(q, it, q_ref, it_ref):
     return float(same.mean()), float(dq.max()), float(dq[clean].max()) if clean.any() else 0.0
 
 
-def emu_retarget_batch_ex(robot, table, pos, quat, ratio, lengths=None, bits=64, flags=0, qpos_init=None, warm_state=None):
-    """Emulator with the GmrBatchExtra members: returns (qpos, iters, local_body_pos, lowest_z, warm_state)."""
+def emu_retarget_batch_ex(robot, table, pos, quat, ratio, lengths=None, bits=64, flags=0, qpos_init=None, warm_state=None,
+                          status=None):
+    """Emulator with the GmrBatchExtra members: returns (qpos, iters, local_body_pos, lowest_z, warm_state);
+    `status` (int32 [C], zeroed by the caller) receives the per-clip GMR_STATUS_* words."""
     from general_motion_retargeting_b200._native import GmrBatchExtra
     global _emu
     if _emu is None:
@@ -69,7 +71,8 @@ def emu_retarget_batch_ex(robot, table, pos, quat, ratio, lengths=None, bits=64,
     ratio = np.ascontiguousarray(ratio, np.float32)
     ln = None if lengths is None else np.ascontiguousarray(lengths, np.int32)
     qi = None if qpos_init is None else np.ascontiguousarray(qpos_init, np.float64)
-    ex = GmrBatchExtra(None if ln is None else ln.ctypes.data, lbp.ctypes.data, low.ctypes.data, warm.ctypes.data)
+    ex = GmrBatchExtra(None if ln is None else ln.ctypes.data, lbp.ctypes.data, low.ctypes.data, warm.ctypes.data,
+                       None if status is None else status.ctypes.data)
     rc = _emu.gmr_emu_retarget_batch_ex(
         C.byref(desc), C.c_void_p(pos.ctypes.data), C.c_void_p(quat.ctypes.data), C.c_void_p(ratio.ctypes.data), Cn, T,
         None if qi is None else C.c_void_p(qi.ctypes.data), C.c_void_p(qpos.ctypes.data), C.c_void_p(iters.ctypes.data),

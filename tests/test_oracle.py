@@ -195,10 +195,12 @@ def test_oracle_traces_fixture_is_reproducible(built):
     """tests/golden/oracle_traces.npz (the known-answer vectors of the GPU tests) = today's oracle."""
     from oracle import native
     g = np.load(os.path.join(GOLD, "oracle_traces.npz"))
+    from general_motion_retargeting_b200._native import LIE_EPS_ROUND1
     for key in sorted({k.rsplit(".", 1)[0] for k in g.files}):
         src, robot = key.split("_", 1)
         m, tt, _ = problem(src, robot)
         ratio = (g[key + ".heights"].astype(np.float64) / float(tt.height_assumption)).astype(np.float32)
-        q, it, err = native.retarget_batch(m, tt, g[key + ".pos"], g[key + ".quat"], ratio)
-        np.testing.assert_array_equal(it, g[key + ".iters"])
-        np.testing.assert_allclose(q, g[key + ".qpos"], atol=1e-9)
+        for suffix, eps in (("", 0.0), ("_eps10", LIE_EPS_ROUND1)):           # both values of the Lie threshold
+            q, it, err = native.retarget_batch(m, tt, g[key + ".pos"], g[key + ".quat"], ratio, lie_eps=eps)
+            np.testing.assert_array_equal(it, g[key + ".iters" + suffix])
+            np.testing.assert_allclose(q, g[key + ".qpos" + suffix], atol=1e-9)

@@ -26,6 +26,7 @@ OUT = os.path.join(ROOT, "tests", "golden")
 from general_motion_retargeting_b200 import params  # noqa: E402
 from general_motion_retargeting_b200.ik_config import compile_task_table  # noqa: E402
 from general_motion_retargeting_b200.synthetic import make_clips  # noqa: E402
+from general_motion_retargeting_b200._native import LIE_EPS_ROUND1  # noqa: E402
 
 
 def load_reference_modules():
@@ -135,17 +136,21 @@ def golden_oracle_traces():
         m, c, _ = params.load_pack(src, robot)
         tt = compile_task_table(m, c)
         clips = make_clips(m, tt, ids, T=T, src_human=src, stress=stress)
+        # the Lie threshold is a parameter (GmrModelDesc.lie_eps): traces for the default (1e-10) and for round 1's 10 eps
         q, it, err = native.retarget_batch(m, tt, clips.pos, clips.quat, clips.ratio(tt))
+        q1, it1, err1 = native.retarget_batch(m, tt, clips.pos, clips.quat, clips.ratio(tt), lie_eps=LIE_EPS_ROUND1)
         key = f"{src}_{robot}"
         out[key + ".pos"], out[key + ".quat"], out[key + ".heights"] = clips.pos, clips.quat, clips.heights
         out[key + ".qpos"], out[key + ".iters"], out[key + ".err"] = q, it, err
+        out[key + ".qpos_eps10"], out[key + ".iters_eps10"], out[key + ".err_eps10"] = q1, it1, err1
         print(f"  oracle trace {key}: solves/frame {it.sum(-1).mean():.2f}")
     np.savez_compressed(os.path.join(OUT, "oracle_traces.npz"), **out)
 
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    km_mod, mr_mod = load_reference_modules()
-    print("reference FK:"); golden_reference_fk(km_mod)
-    print("reference preprocessing:"); golden_reference_preprocess(mr_mod)
+    if "--oracle-only" not in sys.argv:
+        km_mod, mr_mod = load_reference_modules()
+        print("reference FK:"); golden_reference_fk(km_mod)
+        print("reference preprocessing:"); golden_reference_preprocess(mr_mod)
     print("oracle traces:"); golden_oracle_traces()
