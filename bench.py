@@ -131,44 +131,75 @@ def load_problem(args):
     return robot, compile_task_table(robot, cfg)
 
 
-def cpu_reference_run(robot, table, clips, nthreads=0):
-    """The reference's CPU path for this workload: mink/mujoco/daqp are not installable here, so
-    the float64 C++ oracle port stands in (kind = "port"), on all host threads."""
+def workload_config(args, table):
+    """The `config` object of BOTH arms (identical by construction: the driver compares them)."""
+    C, T = args.clips, args.frames
+    in_mb = C * T * table.nh * 7 * 4 / 1e6
+    return {"workload": f"{args.robot} ({args.src} mapping), {C} synthetic clips x {T} frames per GPU, "
+                        "sequential two-stage IK warm-started per clip (BASELINE.json configs[1])",
+            "clips_per_gpu": C, "frames": T, "sharding": "clips, contiguous ranges per rank, no collective",
+            "l2": f"inputs ~{in_mb:.0f} MB per step {'>' if in_mb > 126 else '<= (reduced-size run: L2 not flushed)'} 126 MB L2"}
+
+
+def cpu_reference_run(robot, table, clips, nthreads=0, src=None, robot_name=None):
+    """The reference's CPU path for this workload on all host threads.  With mink/mujoco/daqp and the reference
+    package importable (oracle/mink_adapter.py, e.g. from baseline/_ref/) the UNMODIFIED reference loop runs, one clip
+    per worker process (kind = "reference"); otherwise the float64 C++ oracle port stands in (kind = "port").
+    Returns (qpos, iters, seconds, kind, note)."""
+    from oracle import mink_adapter
+    ok, why = mink_adapter.available()
+    if ok and src is not None:
+        q, it, _, dt = mink_adapter.retarget_batch(src, robot_name, table.human_names, clips.pos, clips.quat, clips.heights)
+        return q, it, dt, "reference", "unmodified reference loop (" + why + ")"
     from oracle import native
     t0 = time.perf_counter()
     q, it, err = native.retarget_batch(robot, table, clips.pos, clips.quat, clips.ratio(table), nthreads=nthreads)
     dt = time.perf_counter() - t0
-    return q, it, dt
+    return q, it, dt, "port", "float64 C++ oracle port (real reference unavailable: " + why + ")"
 
 
 def main_reference(args):
+    """CPU arm on the SAME workload as the GPU arm (same generator, robot, clip ids 0..C-1, T).  One step = one pass over a
+    bounded, rotating sample of those clips (step k takes the next `sample` clip ids, wrapping around), sized from a
+    short probe so that warm-up + K steps take about two minutes whatever the host and whichever implementation runs."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from general_motion_retargeting_b200.synthetic import make_clips
     robot, table = load_problem(args)
     cores = os.cpu_count() or 1
-    sample = max(32 * cores, 64)         # a few seconds of CPU work per step; enough clips per thread that the tail does not dominate
-    clips = make_clips(robot, table, range(sample), T=args.frames, src_human=args.src)
+    C, T = args.clips, args.frames
+    sub = lambda b, ids: type(b)(pos=b.pos[ids], quat=b.quat[ids], heights=b.heights[ids], qpos_gen=b.qpos_gen[ids])
+    run = lambda b: cpu_reference_run(robot, table, b, src=args.src, robot_name=args.robot)
+    # probe: the first 2 clips per core (at most 64) give the rate of whichever implementation is present
+    n_probe = min(C, max(2 * cores, 8), 64)
+    probe = make_clips(robot, table, range(n_probe), T=T, src_human=args.src)
+    _, _, dt, kind, note = run(probe)
+    rate = n_probe * T / dt
+    budget_s = float(os.environ.get("GMR_REF_BUDGET_S", "120"))
+    passes = max(args.steps + max(args.warmup, 0), 1)
+    sample = int(min(C, max(cores, rate * budget_s / passes / T)))
+    n_gen = min(C, sample * passes)                       # only the clips some pass will touch are generated
+    clips = probe if n_gen <= n_probe else make_clips(robot, table, range(n_gen), T=T, src_human=args.src)
+    n_gen = clips.pos.shape[0]
+    ids_of = lambda k: [(k * sample + i) % n_gen for i in range(sample)]
+    k = 0
     for _ in range(max(args.warmup, 0)):
-        cpu_reference_run(robot, table, clips)
+        run(sub(clips, ids_of(k))); k += 1
     times = []
     for _ in range(args.steps):
-        _, _, dt = cpu_reference_run(robot, table, clips)
+        _, _, dt, _, _ = run(sub(clips, ids_of(k))); k += 1
         times.append(dt)
     tot = sum(times)
-    value = sample * args.frames * args.steps / tot
+    value = sample * T * args.steps / tot
     line = {
         "metric": METRIC if args.robot == "unitree_g1" else f"retargeted frames/sec ({args.robot})", "value": value, "unit": "frames/s", "impl": "reference",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.robot} ({args.src}), {sample} synthetic clips x {args.frames} frames per step "
-                               f"(bounded sample of the 4096-clip workload), two-stage IK, CPU",
-                   "clips_per_step": sample, "frames": args.frames},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} clips x {args.frames} frames per step, {args.steps} steps, "
-                                   f"float64 C++ oracle port on {cores} host threads "
-                                   "(mink/mujoco/daqp are not installable offline)"},
+        "config": workload_config(args, table),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
+                         "sample": f"each step = {sample} of the workload's {C} clips x {T} frames (rotating window over clip ids "
+                                   f"0..{n_gen - 1}), {args.steps} steps; {note}; {cores} host threads"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "published_reference_fps_single_process": "35-70 (README.md:215-221, desktop CPUs)",
     }
@@ -314,9 +345,9 @@ def main_ours(args):
         sample = min(C, max(64 * cores, 64))      # ~10 s of CPU work on the box's host cores
         sub = type(clips)(pos=clips.pos[:sample], quat=clips.quat[:sample], heights=clips.heights[:sample],
                           qpos_gen=clips.qpos_gen[:sample])
-        q_ref, it_ref, dt = cpu_reference_run(robot, table, sub)
-        cpu_baseline = {"value": sample * T / dt, "unit": "frames/s", "cores": cores, "kind": "port",
-                        "sample": f"first {sample} clips x {T} frames of the same workload, float64 C++ oracle port, "
+        q_ref, it_ref, dt, kind, note = cpu_reference_run(robot, table, sub)      # the port: the parity sample needs seconds, not hours
+        cpu_baseline = {"value": sample * T / dt, "unit": "frames/s", "cores": cores, "kind": kind,
+                        "sample": f"first {sample} clips x {T} frames of the same workload, {note}, "
                                   f"{cores} host threads, {dt:.1f} s"}
         same = (iters[:sample] == it_ref).all(-1)
         dq = np.abs(q_gpu_sample[:sample] - q_ref).max(-1)
@@ -325,6 +356,22 @@ def main_ours(args):
                   "max_abs_dqpos_all": float(dq.max()),
                   "max_abs_dqpos_identical_history": float(dq[prefix].max()) if prefix.any() else None,
                   "p999_abs_dqpos": float(np.quantile(dq, 0.999)), "vs": "float64 CPU oracle (oracle/gmr_oracle.cpp)"}
+        # the real thing, when it can run here (oracle/mink_adapter.py): one clip per core, first 60 frames
+        from oracle import mink_adapter
+        ok, why = mink_adapter.available()
+        if ok:
+            n, tt = min(cores, C, 16), min(T, 60)
+            q_m, it_m, _, dt_m = mink_adapter.retarget_batch(args.src, args.robot, table.human_names, clips.pos[:n, :tt],
+                                                            clips.quat[:n, :tt], clips.heights[:n])
+            same = (iters[:n, :tt] == it_m).all(-1)
+            dq = np.abs(q_gpu_sample[:n, :tt] - q_m).max(-1)
+            prefix = np.logical_and.accumulate(same, axis=1)
+            parity["vs_unmodified_reference"] = {
+                "frames": int(same.size), "iteration_count_agreement": float(same.mean()), "max_abs_dqpos_all": float(dq.max()),
+                "max_abs_dqpos_identical_history": float(dq[prefix].max()) if prefix.any() else None,
+                "frames_per_s": n * tt / dt_m, "what": why}
+        else:
+            parity["vs_unmodified_reference"] = {"unavailable": why}
 
     if rank == 0:
         peaks = {}
@@ -358,11 +405,8 @@ def main_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"{args.robot} ({args.src} mapping), {C} synthetic clips x {T} frames per GPU, "
-                                   "sequential two-stage IK warm-started per clip (BASELINE.json configs[1])",
-                       "clips_per_gpu": C, "frames": T, "sharding": "clips, contiguous ranges per rank, no collective",
-                       "l2": (lambda mb: f"inputs {mb:.0f} MB per step {'>' if mb > 126 else '<= (reduced-size run: L2 not flushed)'} 126 MB L2")((clips.pos.nbytes + clips.quat.nbytes) / 1e6),
-                       "solves_per_frame": float(iters.sum() / (C * T))},
+            "config": workload_config(args, table),
+            "solves_per_frame": float(iters.sum() / (C * T)),
             "gpu_launches": int(launches),
             "clocks": clocks,
             "e2e": e2e,

@@ -202,7 +202,6 @@ gmr_finalize_kernel(const float* __restrict__ qpos, const float* __restrict__ lo
   }
 }
 
-constexpr int QUEUE_RING = 256;
 // Mixed-robot batches (BASELINE.json configs[4]): ONE launch serves up to GMR_MAX_MULTI robot-uniform buckets.  The
 // CTAs are divided among the buckets in proportion to their work; a CTA stages its bucket's constant block and
 // copies the bucket's dims / scalars / batch pointers from the kernel parameters into shared memory (they cannot
@@ -273,8 +272,11 @@ struct GmrModel {
   GmrScal<float> ks32{};
   GmrScal<double> ks64{};
   int wel32 = 0, wel64 = 0;      // per-warp shared-memory elements
-  int* d_queue = nullptr;        // ring of clip-queue counters, one per launch in flight
-  std::atomic<uint32_t> queue_next{0};
+  // Stream-ordered scratch (clip-queue counters, clip permutations, the two-phase hand-over state) comes from the
+  // model's OWN memory pool with an unlimited release threshold: the device's default pool gives freed memory back to
+  // the OS at every synchronisation, and a caller that synchronises after each call (e.g. to read the status words)
+  // then pays a fresh OS allocation per call — measured: 80 ms calls turning into 0.5-1 s ones.
+  cudaMemPool_t pool = nullptr;
   // lazily created resources of the host-buffer entry
   std::mutex host_mu;
   cudaStream_t hs[2] = {nullptr, nullptr};
@@ -293,11 +295,12 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-// stream-ordered scratch memory (cudaMallocAsync) released in stream order when the scope ends
+// stream-ordered scratch memory from the model's pool, released in stream order when the scope ends: every launch
+// in flight owns its counters and lists, whatever the number of streams or the depth of the queue
 struct StreamScratch {
-  cudaStream_t st; char* p = nullptr;
-  explicit StreamScratch(cudaStream_t s) : st(s) {}
-  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(reinterpret_cast<void**>(&p), bytes, st); }
+  cudaMemPool_t pool; cudaStream_t st; char* p = nullptr;
+  StreamScratch(cudaMemPool_t pl, cudaStream_t s) : pool(pl), st(s) {}
+  cudaError_t alloc(size_t bytes) { return cudaMallocFromPoolAsync(reinterpret_cast<void**>(&p), bytes, pool, st); }
   ~StreamScratch() { if (p) { cudaFreeAsync(p, st); } }
   StreamScratch(const StreamScratch&) = delete;
   StreamScratch& operator=(const StreamScratch&) = delete;
@@ -361,7 +364,6 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
   io.pos = pos; io.quat = quat; io.ratio = ratio; io.qinit = qinit; io.qout = qout; io.iters = iters; io.err = err; io.tg = tg;
   io.C = C; io.T = T; io.flags = flags & 0xffffu; io.ex = ex;
   const GmrDims& dims = sizeof(R) == 4 ? m->dims32 : m->dims64;
-  auto next_queue = [&]() { return m->d_queue + 4 * (m->queue_next.fetch_add(1) % QUEUE_RING); };
   const int slots = grid * wpc;
   static const int lpt_env = getenv("GMR_LPT") ? atoi(getenv("GMR_LPT")) : 1;
   // warps per slow SM (0 = off) and share of the SMs the slow clips may take: measured optima on the benchmark mix
@@ -376,14 +378,13 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
   if (two_phase) {
     const int stride = gmr_state_stride(dims.nq);
     const size_t b_state = ((size_t)C * stride * sizeof(double) + 255) & ~(size_t)255, b_order = (size_t)2 * C * sizeof(int);
-    StreamScratch scratch(st);                               // freed in stream order on every exit path
-    CK(scratch.alloc(b_state + b_order));
-    double* state = reinterpret_cast<double*>(scratch.p);
-    int* order2 = reinterpret_cast<int*>(scratch.p + b_state);
-    int* q1 = next_queue();
-    int* q2 = next_queue();
-    CK(cudaMemsetAsync(q1, 0, 4 * sizeof(int), st));
-    CK(cudaMemsetAsync(q2, 0, 4 * sizeof(int), st));
+    StreamScratch scratch(m->pool, st);                      // freed in stream order on every exit path
+    CK(scratch.alloc(256 + b_state + b_order));              // [ two clip queues | state | lists ]
+    int* q1 = reinterpret_cast<int*>(scratch.p);
+    int* q2 = q1 + 4;
+    double* state = reinterpret_cast<double*>(scratch.p + 256);
+    int* order2 = reinterpret_cast<int*>(scratch.p + 256 + b_state);
+    CK(cudaMemsetAsync(q1, 0, 8 * sizeof(int), st));
     // launch A: frame 0 of every clip (balanced work: every clip starts from the same configuration)
     GmrIO<IO> ioa = io;
     ioa.t_begin = 0; ioa.t_end = 1; ioa.state = state;
@@ -401,14 +402,15 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
     return GMR_OK;
   }
 
-  int* queue = own_queue ? own_queue : next_queue();
+  // more clips than warp slots: hard clips first (stream-ordered scratch for the clip queue and the permutation)
+  const bool lpt = lpt_env && C > slots;
+  StreamScratch scratch(m->pool, st);
+  if (!own_queue || lpt) CK(scratch.alloc(256 + (lpt ? (size_t)2 * C * sizeof(int) : 0)));
+  int* queue = own_queue ? own_queue : reinterpret_cast<int*>(scratch.p);
   CK(cudaMemsetAsync(queue, 0, 4 * sizeof(int), st));
-  // more clips than warp slots: hard clips first (stream-ordered scratch for the permutation)
   int* order = nullptr;
-  StreamScratch scratch(st);
-  if (lpt_env && C > slots) {
-    CK(scratch.alloc((size_t)2 * C * sizeof(int)));
-    order = reinterpret_cast<int*>(scratch.p);
+  if (lpt) {
+    order = reinterpret_cast<int*>(scratch.p + 256);
     gmr_order_kernel<R, IO><<<(C + 255) / 256, 256, 0, st>>>(dc, quat, qinit, C, T, queue + 1, order);
     g_launches.fetch_add(1);
     CK(cudaGetLastError());
@@ -447,7 +449,13 @@ int gmr_model_create(const GmrModelDesc* desc, int device, GmrModel** out) {
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   if (e == cudaSuccess) e = cudaMalloc(&m->d_f32, consts_bytes<float>());
   if (e == cudaSuccess) e = cudaMalloc(&m->d_f64, consts_bytes<double>());
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_queue, QUEUE_RING * 4 * sizeof(int));
+  if (e == cudaSuccess) {
+    cudaMemPoolProps pp{};
+    pp.allocType = cudaMemAllocationTypePinned; pp.handleTypes = cudaMemHandleTypeNone;
+    pp.location.type = cudaMemLocationTypeDevice; pp.location.id = device;
+    e = cudaMemPoolCreate(&m->pool, &pp);
+    if (e == cudaSuccess) { uint64_t keep = UINT64_MAX; e = cudaMemPoolSetAttribute(m->pool, cudaMemPoolAttrReleaseThreshold, &keep); }
+  }
   if (e == cudaSuccess) e = cudaMemset(m->d_f32, 0, consts_bytes<float>());
   if (e == cudaSuccess) e = cudaMemset(m->d_f64, 0, consts_bytes<double>());
   if (e == cudaSuccess) e = cudaMemcpy(m->d_f32, &m->h_f32, sizeof(GmrConsts<float>), cudaMemcpyHostToDevice);
@@ -457,12 +465,12 @@ int gmr_model_create(const GmrModelDesc* desc, int device, GmrModel** out) {
     int code = cuda_err(e, "gmr_model_create");
     if (m->d_f32) cudaFree(m->d_f32);
     if (m->d_f64) cudaFree(m->d_f64);
-    if (m->d_queue) cudaFree(m->d_queue);
+    if (m->pool) cudaMemPoolDestroy(m->pool);
     delete m;
     return code;
   }
   if (smem_bytes<float>(m, 1) > (size_t)m->max_smem) {
-    cudaFree(m->d_f32); cudaFree(m->d_f64); cudaFree(m->d_queue); delete m;
+    cudaFree(m->d_f32); cudaFree(m->d_f64); cudaMemPoolDestroy(m->pool); delete m;
     return set_err(GMR_ELIMIT, "model does not fit in shared memory");
   }
   *out = m;
@@ -478,7 +486,7 @@ int gmr_model_destroy(GmrModel* m) {
   }
   cudaFree(m->d_f32);
   cudaFree(m->d_f64);
-  cudaFree(m->d_queue);
+  if (m->pool) cudaMemPoolDestroy(m->pool);      // outstanding stream-ordered frees complete first (CUDA defers the release)
   delete m;
   return GMR_OK;
 }
@@ -577,11 +585,12 @@ int launch_multi(const GmrBatchDesc* b, int n, uint32_t flags, cudaStream_t st) 
   if (grid < n) return set_err(GMR_ELIMIT, "more buckets than SMs");
   GmrMultiArgs<R, float> mu{};
   mu.n = n;
-  StreamScratch scratch(st);
+  StreamScratch scratch(m0->pool, st);
   size_t order_ints = 0;
   for (int i = 0; i < n; i++) order_ints += (size_t)2 * b[i].C;
-  CK(scratch.alloc(order_ints * sizeof(int)));
-  int* order_base = reinterpret_cast<int*>(scratch.p);
+  CK(scratch.alloc(256 + order_ints * sizeof(int)));       // [ one clip queue per bucket | lists ]
+  CK(cudaMemsetAsync(scratch.p, 0, 256, st));
+  int* order_base = reinterpret_cast<int*>(scratch.p + 256);
   int assigned = 0;
   double acc = 0;
   for (int i = 0; i < n; i++) {
@@ -598,8 +607,7 @@ int launch_multi(const GmrBatchDesc* b, int n, uint32_t flags, cudaStream_t st) 
     GmrIO<float>& io = mu.io[i];
     io.pos = b[i].pos; io.quat = b[i].quat; io.ratio = b[i].ratio; io.qinit = b[i].qpos_init; io.qout = b[i].qpos_out;
     io.iters = b[i].iters_out; io.err = b[i].err_out; io.tg = nullptr; io.C = b[i].C; io.T = b[i].T; io.flags = flags & 0xffffu;
-    int* q = m0->d_queue + 4 * (m0->queue_next.fetch_add(1) % QUEUE_RING);
-    CK(cudaMemsetAsync(q, 0, 4 * sizeof(int), st));
+    int* q = reinterpret_cast<int*>(scratch.p) + 4 * i;
     mu.queue[i] = q;
     // hard clips first within each bucket (same pre-pass as the single-robot path)
     gmr_order_kernel<R, float><<<(b[i].C + 255) / 256, 256, 0, st>>>(mu.gc[i], b[i].quat, b[i].qpos_init, b[i].C, b[i].T, q + 1, order_base);

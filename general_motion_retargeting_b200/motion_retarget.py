@@ -106,6 +106,7 @@ class GeneralMotionRetargeting:
         verbose: bool = False,
         device: Union[int, str, None] = None,
         precision: str = "f64",
+        lie_eps: Optional[float] = None,
     ) -> None:
         # the robot model and IK config (KeyError on unknown names, like the reference's dict lookups).  xml_file is the
         # MJCF path callers hand to KinematicsModel (smplx_to_robot_dataset.py:94); the model itself comes from the
@@ -125,6 +126,9 @@ class GeneralMotionRetargeting:
         if precision not in ("f32", "f64"):
             raise ValueError("precision must be 'f32' or 'f64'")
         self.precision = precision
+        # mink's small-angle threshold of SO3/SE3 log and jlog (GmrModelDesc.lie_eps; None = 1e-10, the value recalled
+        # for mink's float64 get_epsilon; round 1 assumed 10 eps = 2.2e-15 — DESIGN.md §5 records what moves between them)
+        self.lie_eps = float(lie_eps) if lie_eps else 0.0
         self.src_human, self.tgt_robot = src_human, tgt_robot
 
         # height ratio (motion_retarget.py:36-43)
@@ -182,7 +186,7 @@ class GeneralMotionRetargeting:
     def _handle(self, device: int) -> _Handle:
         h = self._handles.get(device)
         if h is None:
-            desc, keep = _native.build_desc(self._robot, self._table, damping=self.damping, max_iter=self.max_iter)
+            desc, keep = _native.build_desc(self._robot, self._table, damping=self.damping, max_iter=self.max_iter, lie_eps=self.lie_eps)
             h = _Handle(self._lib, desc, device)
             del keep
             self._handles[device] = h

@@ -15,7 +15,7 @@ cache = "/tmp/mix_%d_%d.npz" % (C, T)
 if os.path.exists(cache):
     z = np.load(cache); pos, quat, h = z["pos"], z["quat"], z["h"]
 else:
-    b = make_clips(robot, table, range(C), T=T); pos, quat, h = b.pos, b.quat, b.heights
+    b = make_clips(robot, table, range(C), T=T, device="cuda"); pos, quat, h = b.pos, b.quat, b.heights
     np.savez(cache, pos=pos, quat=quat, h=h)
 dp, dq, dh = (torch.from_numpy(x).cuda() for x in (pos, quat, h))
 out = {"env": {k: v for k, v in os.environ.items() if k.startswith("GMR_")}}
