@@ -324,6 +324,7 @@ def main_ours(args):
         n_pos, n_quat, n_out = p_pos.numpy(), p_quat.numpy(), p_out.numpy()
         for _ in range(max(1, min(args.warmup, 2))):
             gmr.retarget_batch(n_pos, n_quat, clips.heights, out=n_out, precision=args.precision)
+        n_out.fill(np.nan)                    # the timed steps must produce every value they are credited with
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -333,7 +334,10 @@ def main_ours(args):
         e2e = {"value": frames_step_all * args.steps / e2e_s, "unit": "frames/s",
                "h2d_bytes_per_step": int(n_pos.nbytes + n_quat.nbytes + clips.heights.nbytes),
                "d2h_bytes_per_step": int(n_out.nbytes), "ms_per_step": 1e3 * e2e_s / args.steps,
-               "api": "GeneralMotionRetargeting.retarget_batch(numpy pinned, float32 buffers) -> gmr_retarget_batch_host"}
+               "api": "GeneralMotionRetargeting.retarget_batch(numpy arrays in pinned host memory, float32) -> "
+                      "gmr_retarget_batch_host_ex; the kernel reads the keypoints over the host link (TMA bulk copies from "
+                      "the mapped arrays, one frame ahead) and writes qpos into the caller's array: the bytes below cross "
+                      "the link inside the timed region, every step; wall clock around the calls, max over ranks"}
         e2e_check = float(np.abs(n_out[: q_gpu_sample.shape[0]].astype(np.float64) - q_gpu_sample).max())
     else:
         e2e_check = None

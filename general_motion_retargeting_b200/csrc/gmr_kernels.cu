@@ -121,6 +121,7 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
   const int wel = dm.warp_elems;
   WarpSolver<R> ws(*mc, dm, ks, (uint32_t)(16 + CB) + (uint32_t)warp * (uint32_t)wel * (uint32_t)sizeof(R), lane);
+  ws.stream_init();
   ws.convoy = (kflags & GMR_FLAG_INTERNAL_CONVOY) != 0;
   const int C = io.C;
   ws.cta_active = reinterpret_cast<int*>(smem + 8);                  // second half of the mbarrier's 16-byte slot
@@ -242,6 +243,7 @@ gmr_retarget_multi_kernel(const __grid_constant__ GmrMultiArgs<R, IO> mu) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
   const GmrDims& dm = loc->dm;
   WarpSolver<R> ws(*mc, dm, *ks, (uint32_t)(16 + CB + LB) + (uint32_t)warp * (uint32_t)dm.warp_elems * (uint32_t)sizeof(R), lane);
+  ws.stream_init();
   const int C = io->C, lb = (int)blockIdx.x - loc->cta_begin, lg = loc->cta_count;
   int* queue = mu.queue[r];
   const int* order = mu.order[r];
@@ -280,8 +282,6 @@ struct GmrModel {
   // lazily created resources of the host-buffer entry
   std::mutex host_mu;
   cudaStream_t hs[2] = {nullptr, nullptr};
-  void* hbuf[2] = {nullptr, nullptr};
-  size_t hbuf_bytes[2] = {0, 0};
 };
 
 namespace {
@@ -482,7 +482,6 @@ int gmr_model_destroy(GmrModel* m) {
   DeviceGuard g(m->device);
   for (int i = 0; i < 2; i++) {
     if (m->hs[i]) { cudaStreamSynchronize(m->hs[i]); cudaStreamDestroy(m->hs[i]); }
-    if (m->hbuf[i]) cudaFree(m->hbuf[i]);
   }
   cudaFree(m->d_f32);
   cudaFree(m->d_f64);
@@ -786,12 +785,91 @@ int gmr_stream_retarget(GmrStream* s, const float* pos, const float* quat, uint3
   return GMR_OK;
 }
 
-// Host-buffer entry: clips are cut into chunks; chunk i+1's host->device copy and chunk i-1's
-// device->host copy overlap chunk i's solve on two streams with private staging buffers.
+// Host-buffer entry.  Page-locked (pinned) host arrays are used IN PLACE: the solve kernel pulls each frame's keypoints
+// over the host link with TMA bulk copies one frame ahead of the solve (it needs ~6 GB/s of a link that serves > 30 GB/s
+// of such requests, tools/microbench/pcie.cu) and writes each frame's qpos straight into the caller's array, so the
+// transfers ride inside the solve instead of in front of and behind it, and the whole batch is ONE schedule (two-phase
+// partition included) — cutting clips into chunks to overlap copies would make every chunk pay its own tail.
+// Pageable arrays cannot be mapped: they are staged through stream-ordered device scratch (cudaMemcpyAsync before /
+// after the solve), in chunks of whole waves only when the staging would exceed a memory budget.
 int gmr_retarget_batch_host(GmrModel* m, const float* pos, const float* quat, const float* ratio, int32_t C, int32_t T,
                             const float* qpos_init, float* qpos_out, int32_t* iters_out, float* err_out, uint32_t flags) {
   return gmr_retarget_batch_host_ex(m, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out, nullptr, flags);
 }
+
+}  // extern "C"
+
+namespace {
+// device-visible alias of a host array, or null when the array is pageable
+void* mapped_alias(const void* h) {
+  if (!h) return nullptr;
+  static const bool off = getenv("GMR_HOST_STAGED") && atoi(getenv("GMR_HOST_STAGED")) != 0;     // A/B knob: always stage
+  if (off) return nullptr;
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, h) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+  if (a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged || a.type == cudaMemoryTypeDevice) return a.devicePointer;
+  return nullptr;
+}
+
+struct HostArr {
+  const void* h_in = nullptr;   // input array on the host (or null)
+  void* h_out = nullptr;        // output array on the host (or null)
+  size_t per_clip = 0;          // bytes per clip
+  char* alias = nullptr;        // device-visible alias of the whole array (pinned memory), else staged
+  char* dev = nullptr;          // device pointer for the current chunk
+  bool present() const { return h_in || h_out; }
+  const char* host() const { return h_in ? (const char*)h_in : (const char*)h_out; }
+};
+
+int host_run(GmrModel* m, HostArr (&arr)[8], int C, int T, uint32_t flags) {
+  enum { A_POS, A_QUAT, A_RATIO, A_INIT, A_Q, A_IT, A_ERR, A_ST };
+  size_t staged_per_clip = 0;
+  for (auto& a : arr) if (a.present()) { a.alias = (char*)mapped_alias(a.host()); if (!a.alias) staged_per_clip += a.per_clip; }
+  const int wave = m->num_sms * ((flags & GMR_FLAG_COMPUTE_F64) ? pick_wpc<double>(m, C) : pick_wpc<float>(m, C));
+  const size_t budget = (size_t)8 << 30;
+  int chunk = C;
+  while ((size_t)chunk * staged_per_clip > budget && chunk > wave) chunk -= wave;
+  for (int i = 0; i < 2; i++) if (!m->hs[i]) CK(cudaStreamCreateWithFlags(&m->hs[i], cudaStreamNonBlocking));
+  if (arr[A_ST].present() && arr[A_ST].alias) memset(arr[A_ST].h_out, 0, (size_t)C * 4);   // mapped status words: bits are OR-ed in
+  int k = 0;
+  for (int c0 = 0; c0 < C; c0 += chunk, k ^= 1) {
+    const int n = (C - c0 < chunk) ? C - c0 : chunk;
+    cudaStream_t st = m->hs[k];
+    StreamScratch scratch(m->pool, st);
+    size_t total = 0;
+    auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    for (auto& a : arr) if (a.present() && !a.alias) total += pad(a.per_clip * n);
+    if (total) CK(scratch.alloc(total));
+    size_t o = 0;
+    for (auto& a : arr) {
+      if (!a.present()) { a.dev = nullptr; continue; }
+      if (a.alias) { a.dev = a.alias + a.per_clip * c0; continue; }
+      a.dev = scratch.p + o; o += pad(a.per_clip * n);
+      if (a.h_in) CK(cudaMemcpyAsync(a.dev, (const char*)a.h_in + a.per_clip * c0, a.per_clip * n, cudaMemcpyHostToDevice, st));
+    }
+    GmrBatchExtra ex{};
+    if (arr[A_ST].present()) {
+      ex.status = (int32_t*)arr[A_ST].dev;
+      if (!arr[A_ST].alias) CK(cudaMemsetAsync(arr[A_ST].dev, 0, (size_t)n * 4, st));
+    }
+    int rc;
+    if (flags & GMR_FLAG_COMPUTE_F64)
+      rc = launch<double, float, MAXW_F64>(m, m->d_f64, (const float*)arr[A_POS].dev, (const float*)arr[A_QUAT].dev, (const float*)arr[A_RATIO].dev,
+                                           n, T, (const float*)arr[A_INIT].dev, (float*)arr[A_Q].dev, (int32_t*)arr[A_IT].dev,
+                                           (float*)arr[A_ERR].dev, nullptr, flags, st, &ex);
+    else
+      rc = launch<float, float, MAXW_F32>(m, m->d_f32, (const float*)arr[A_POS].dev, (const float*)arr[A_QUAT].dev, (const float*)arr[A_RATIO].dev,
+                                          n, T, (const float*)arr[A_INIT].dev, (float*)arr[A_Q].dev, (int32_t*)arr[A_IT].dev,
+                                          (float*)arr[A_ERR].dev, nullptr, flags, st, &ex);
+    if (rc != GMR_OK) return rc;
+    for (auto& a : arr)
+      if (a.h_out && !a.alias) CK(cudaMemcpyAsync((char*)a.h_out + a.per_clip * c0, a.dev, a.per_clip * n, cudaMemcpyDeviceToHost, st));
+  }
+  return GMR_OK;
+}
+}  // namespace
+
+extern "C" {
 
 int gmr_retarget_batch_host_ex(GmrModel* m, const float* pos, const float* quat, const float* ratio, int32_t C, int32_t T,
                                const float* qpos_init, float* qpos_out, int32_t* iters_out, float* err_out,
@@ -800,64 +878,24 @@ int gmr_retarget_batch_host_ex(GmrModel* m, const float* pos, const float* quat,
   if (C < 0 || T < 0) return set_err(GMR_EINVAL, "negative batch size");
   if (C == 0 || T == 0) return GMR_OK;
   if (!pos || !quat || !qpos_out) return set_err(GMR_EINVAL, "pos, quat and qpos_out are required");
+  if ((reinterpret_cast<uintptr_t>(quat) & 15u) != 0) return set_err(GMR_EINVAL, "quat must be 16-byte aligned");
   DeviceGuard g(m->device);
   if (!g.ok) return set_err(GMR_ECUDA, "cannot select the model's device");
-  std::lock_guard<std::mutex> lk(m->host_mu);
-  const int nq = m->h_f32.nq, nh = m->h_f32.nhum;
-  // per-clip device bytes (each array padded to 16 bytes per chunk below)
-  const size_t b_pos = (size_t)T * nh * 3 * 4, b_quat = (size_t)T * nh * 4 * 4, b_q = (size_t)T * nq * 4,
-               b_it = iters_out ? (size_t)T * 2 * 4 : 0, b_err = err_out ? (size_t)T * 2 * 4 : 0,
-               b_ratio = ratio ? 4 : 0, b_init = qpos_init ? (size_t)nq * 4 : 0, b_st = status_out ? 4 : 0;
-  const size_t per_clip = b_pos + b_quat + b_q + b_it + b_err + b_ratio + b_init + b_st;
-  // chunks of whole "waves" (one clip per resident warp) so that every chunk fills the GPU
-  const int wave = m->num_sms * ((flags & GMR_FLAG_COMPUTE_F64) ? pick_wpc<double>(m, C) : pick_wpc<float>(m, C));
-  int chunk = C;
-  if (C >= 4 * wave) chunk = ((C / 4 + wave - 1) / wave) * wave;            // >= 4 chunks when there is enough work
-  const size_t budget = (size_t)8 << 30;
-  while ((size_t)chunk * per_clip > budget && chunk > wave) chunk -= wave;
-  for (int i = 0; i < 2; i++) if (!m->hs[i]) CK(cudaStreamCreateWithFlags(&m->hs[i], cudaStreamNonBlocking));
-  int rc = GMR_OK;
-  int k = 0;
-  for (int c0 = 0; c0 < C && rc == GMR_OK; c0 += chunk, k ^= 1) {
-    const int n = (C - c0 < chunk) ? C - c0 : chunk;
-    auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t o_pos = 0, o_quat = o_pos + pad(b_pos * n), o_q = o_quat + pad(b_quat * n), o_it = o_q + pad(b_q * n),
-                 o_err = o_it + pad(b_it * n), o_ratio = o_err + pad(b_err * n), o_init = o_ratio + pad(b_ratio * n),
-                 o_st = o_init + pad(b_init * n), total = o_st + pad(b_st * n);
-    cudaStream_t st = m->hs[k];
-    CK(cudaStreamSynchronize(st));                           // staging buffer k is free again
-    if (m->hbuf_bytes[k] < total) {
-      if (m->hbuf[k]) CK(cudaFree(m->hbuf[k]));
-      m->hbuf[k] = nullptr; m->hbuf_bytes[k] = 0;
-      CK(cudaMalloc(&m->hbuf[k], total));
-      m->hbuf_bytes[k] = total;
-    }
-    char* d = (char*)m->hbuf[k];
-    CK(cudaMemcpyAsync(d + o_pos, pos + (size_t)c0 * T * nh * 3, b_pos * n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d + o_quat, quat + (size_t)c0 * T * nh * 4, b_quat * n, cudaMemcpyHostToDevice, st));
-    if (ratio) CK(cudaMemcpyAsync(d + o_ratio, ratio + c0, b_ratio * n, cudaMemcpyHostToDevice, st));
-    if (qpos_init) CK(cudaMemcpyAsync(d + o_init, qpos_init + (size_t)c0 * nq, b_init * n, cudaMemcpyHostToDevice, st));
-    GmrBatchExtra ex{};
-    if (status_out) { ex.status = (int32_t*)(d + o_st); CK(cudaMemsetAsync(d + o_st, 0, b_st * n, st)); }
-    if (flags & GMR_FLAG_COMPUTE_F64)
-      rc = launch<double, float, MAXW_F64>(m, m->d_f64, (const float*)(d + o_pos), (const float*)(d + o_quat),
-                                           ratio ? (const float*)(d + o_ratio) : nullptr, n, T,
-                                           qpos_init ? (const float*)(d + o_init) : nullptr, (float*)(d + o_q),
-                                           iters_out ? (int32_t*)(d + o_it) : nullptr, err_out ? (float*)(d + o_err) : nullptr,
-                                           nullptr, flags, st, &ex);
-    else
-      rc = launch<float, float, MAXW_F32>(m, m->d_f32, (const float*)(d + o_pos), (const float*)(d + o_quat),
-                                          ratio ? (const float*)(d + o_ratio) : nullptr, n, T,
-                                          qpos_init ? (const float*)(d + o_init) : nullptr, (float*)(d + o_q),
-                                          iters_out ? (int32_t*)(d + o_it) : nullptr, err_out ? (float*)(d + o_err) : nullptr,
-                                          nullptr, flags, st, &ex);
-    if (rc != GMR_OK) break;
-    if (status_out) CK(cudaMemcpyAsync(status_out + c0, d + o_st, b_st * n, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(qpos_out + (size_t)c0 * T * nq, d + o_q, b_q * n, cudaMemcpyDeviceToHost, st));
-    if (iters_out) CK(cudaMemcpyAsync(iters_out + (size_t)c0 * T * 2, d + o_it, b_it * n, cudaMemcpyDeviceToHost, st));
-    if (err_out) CK(cudaMemcpyAsync(err_out + (size_t)c0 * T * 2, d + o_err, b_err * n, cudaMemcpyDeviceToHost, st));
-  }
+  std::lock_guard<std::mutex> lk(m->host_mu);              // the two host-entry streams are the model's
+  const size_t nq = m->h_f32.nq, nh = m->h_f32.nhum;
+  HostArr arr[8];
+  arr[0].h_in = pos;        arr[0].per_clip = (size_t)T * nh * 12;
+  arr[1].h_in = quat;       arr[1].per_clip = (size_t)T * nh * 16;
+  arr[2].h_in = ratio;      arr[2].per_clip = 4;
+  arr[3].h_in = qpos_init;  arr[3].per_clip = nq * 4;
+  arr[4].h_out = qpos_out;  arr[4].per_clip = (size_t)T * nq * 4;
+  arr[5].h_out = iters_out; arr[5].per_clip = (size_t)T * 8;
+  arr[6].h_out = err_out;   arr[6].per_clip = (size_t)T * 8;
+  arr[7].h_out = status_out; arr[7].per_clip = 4;
+  int rc = host_run(m, arr, C, T, flags);
+  // whatever happened, nothing of this call may still be in flight when the caller gets its arrays back
   for (int i = 0; i < 2; i++) {
+    if (!m->hs[i]) continue;
     cudaError_t e = cudaStreamSynchronize(m->hs[i]);
     if (e != cudaSuccess && rc == GMR_OK) rc = cuda_err(e, "cudaStreamSynchronize");
   }

@@ -95,14 +95,18 @@ enum {
   GS_LF = 100,              // [28] base 6x6 Schur complement (21, packed upper) + its right-hand side (6)
   GS_PIV = 128,             // [4]
   GS_RQ = 132,              // [4] normalised root quaternion of the last FK
-  GS_BND = 136,             // [32] bound value of pinned hinges
-  GS_LP = 168,              // [9][32] lane-private slots
-  GS_Q = 168 + 9 * 32,      // [40] qpos
-  GS_VAR = 168 + 9 * 32 + 40
+  GS_BAR = 136,             // [4] mbarrier of the keypoint stream (8 bytes used)
+  GS_BND = 140,             // [32] bound value of pinned hinges
+  GS_LP = 172,              // [9][32] lane-private slots
+  GS_Q = 172 + 9 * 32,      // [40] qpos
+  GS_VAR = 172 + 9 * 32 + 40
 };
 enum { LP_F = 0, LP_DIAG = 6, LP_CI = 7, LP_X = 8 };
 
-template <typename R> GMR_HD int gmr_in_elems(int nhum) { return gmr_pad4((int)((8 * nhum * sizeof(float) + sizeof(R) - 1) / sizeof(R))); }
+// staged raw keypoints of one frame (floats): [ positions nhum x 3, placed at the source's offset within its 16-byte line
+// (<= 3 floats of slack in front, so that the TMA bulk copy of the aligned body lands 16-byte aligned) | quaternions nhum x 4 ]
+GMR_HD constexpr int gmr_in_quat(int nhum) { return gmr_pad4(3 * nhum + 4); }
+template <typename R> GMR_HD int gmr_in_elems(int nhum) { return gmr_pad4((int)(((gmr_in_quat(nhum) + 4 * nhum) * sizeof(float) + sizeof(R) - 1) / sizeof(R))); }
 // variable part: sd[8nh] tg[8nhum] in[staged floats] U, where the union U holds
 //   [ mt: task inertias, max(28 nt, 72) | xp: 4 nb | xq: 4 nb ]          while FK / task evaluation are live, and
 //   [ published factor rows, nh * stride ]                                  from the factorisation to the next FK.
@@ -374,6 +378,10 @@ struct WarpSolver {
   // working set carried from the previous solve of the same STAGE (uniform).  Four scalars, selected by
   // comparison: a dynamically indexed member array would push the whole solver object into local memory.
   uint32_t warm_lo0, warm_hi0, warm_lo1, warm_hi1;
+  // keypoint stream (uniform): float offset of the staged positions inside their slot (= the source frame's offset within
+  // its 16-byte line), whether a frame is in flight, and the phase of the warp's mbarrier
+  uint32_t in_off, in_phase;
+  bool in_flight;
 
 #ifdef GMR_EMULATE
   GMR_FN WarpSolver(const GmrConsts<R>& m, const GmrDims& d, const GmrScal<R>& k, R* smem)
@@ -381,7 +389,8 @@ struct WarpSolver {
   // smem_byte_off: offset of this warp's state block from the start of the dynamic shared window
   GMR_FN WarpSolver(const GmrConsts<R>& m, const GmrDims& d, const GmrScal<R>& k, uint32_t smem_byte_off, int lane)
 #endif
-                     : mc(m), dm(d), ks(k), stat_refactor(0), stat_flags(0), convoy(false), cta_active(nullptr), warm_lo0(0), warm_hi0(0), warm_lo1(0), warm_hi1(0) {
+                     : mc(m), dm(d), ks(k), stat_refactor(0), stat_flags(0), convoy(false), cta_active(nullptr), warm_lo0(0), warm_hi0(0), warm_lo1(0), warm_hi1(0),
+                       in_off(0), in_phase(0), in_flight(false) {
 #ifndef GMR_EMULATE
     lane_ = lane;
     dep_ = lane < d.nh ? (int)m.hdepth[lane] : 0;
@@ -408,6 +417,8 @@ struct WarpSolver {
   GMR_FN R* s_sd() const { return sm + GS_VAR; }
   GMR_FN R* s_tg() const { return sm + dm.o_tg; }
   GMR_FN float* s_in() const { return reinterpret_cast<float*>(sm + dm.o_in); }
+  GMR_FN float* s_inq() const { return s_in() + gmr_in_quat(dm.nhum); }
+  GMR_FN R* s_bar() const { return sm + GS_BAR; }
   GMR_FN R* s_xp() const { return sm + dm.o_xp; }
   GMR_FN R* s_xq() const { return sm + dm.o_xq; }
   GMR_FN R* s_U() const { return sm + dm.o_u; }
@@ -477,20 +488,21 @@ struct WarpSolver {
   }
 
   // ------------------------------------------------------------------ targets (A1-A5) ------
-  // Raw keypoints of one frame (staged in s_in[h] = pos(3) pad quat(4), float) ->
+  // Raw keypoints of one frame (staged by stage_frame: positions at s_in + in_off, quaternions at s_inq, float) ->
   // scaled + offset targets in s_tg[h] = (pos[3], pad, quat[4]).
   // Returns false (uniform) when a keypoint is not finite or a quaternion has no direction: the reference would raise
   // inside scipy / mink on such a frame (and its dataset script would skip the file); the caller stops the clip.
   GMR_FN bool update_targets(R ratio, bool to_ground) {
     bool ok = true;
     GMR_LANES
-      if (lane == dm.hroot) { const float* in = s_in() + 8 * lane; s_red()[0] = R(in[0]); s_red()[1] = R(in[1]); s_red()[2] = R(in[2]); }
+      if (lane == dm.hroot) { const float* in = s_in() + in_off + 3 * lane; s_red()[0] = R(in[0]); s_red()[1] = R(in[1]); s_red()[2] = R(in[2]); }
     GMR_END
     GMR_LANES
       bool fin = true;
       if (lane < dm.nhum) {
         const R rx = s_red()[0], ry = s_red()[1], rz = s_red()[2];
-        const float* in = s_in() + 8 * lane;
+        const float* in = s_in() + in_off + 3 * lane;
+        const float* iq = s_inq() + 4 * lane;
         const R sr = mc.hscale[dm.hroot] * ratio;
         R p[3];
         if (lane == dm.hroot) { p[0] = sr * rx; p[1] = sr * ry; p[2] = sr * rz; }
@@ -498,7 +510,7 @@ struct WarpSolver {
           const R s = mc.hscale[lane] * ratio;
           p[0] = (R(in[0]) - rx) * s + sr * rx; p[1] = (R(in[1]) - ry) * s + sr * ry; p[2] = (R(in[2]) - rz) * s + sr * rz;
         }
-        R q[4] = {R(in[4]), R(in[5]), R(in[6]), R(in[7])};
+        R q[4] = {R(iq[0]), R(iq[1]), R(iq[2]), R(iq[3])};
         const R qn2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
         // NaN fails every comparison; float32 inputs cannot overflow R here
         fin = qn2 > R(1e-30) && qn2 < R(INFINITY) && (g_abs(p[0]) + g_abs(p[1]) + g_abs(p[2])) < R(INFINITY);
@@ -1226,33 +1238,83 @@ struct WarpSolver {
   }
 
   // ------------------------------------------------------------------ keypoint stream -------
-  // Asynchronous copy (cp.async, LDGSTS) of one frame's raw keypoints into the staging area;
-  // frame_wait() must be called before update_targets() reads them.
-  GMR_FN void stage_frame(const float* pos, const float* quat) {
-    GMR_LANES
-      if (lane < dm.nhum) {
-        float* dst = s_in() + 8 * lane;
-        const float* p = pos + 3 * lane;
-        const float* q = quat + 4 * lane;
-#ifdef GMR_EMULATE
-        dst[0] = p[0]; dst[1] = p[1]; dst[2] = p[2];
-        dst[4] = q[0]; dst[5] = q[1]; dst[6] = q[2]; dst[7] = q[3];
-#else
-        const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(p) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 4), "l"(p + 1) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 8), "l"(p + 2) : "memory");
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(q) : "memory");
-#endif
-      }
+  // One frame's raw keypoints (positions nhum x 12 bytes, quaternions nhum x 16 bytes, two arrays) are staged into
+  // shared memory by TMA bulk copies (cp.async.bulk -> UBLKCP) whose completion is counted on the warp's own
+  // mbarrier: one elected lane issues the quaternion block and the 16-byte aligned body of the position block;
+  // frames are 12 nhum bytes apart, so a position block may start 4/8/12 bytes off a 16-byte line: its <= 3 head
+  // and <= 3 tail words travel as 4-byte cp.async (LDGSTS) and the block is placed at the same offset inside its
+  // slot (in_off).  Bulk requests are what the host link serves best when the arrays live in mapped pinned host
+  // memory (gmr_retarget_batch_host reads them in place: tools/microbench/pcie.cu measured 33 GB/s against 22 GB/s
+  // for per-body cp.async; the solve needs 6), and one instruction instead of four per body for arrays in HBM.
+  // frame_wait() must be called before update_targets() reads the frame; one frame is in flight at most.
+  GMR_FN void stream_init() {
 #ifndef GMR_EMULATE
+    if (lane_ == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_bar())));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+#endif
+    in_phase = 0; in_flight = false; in_off = 0;
+  }
+  GMR_FN void stage_frame(const float* pos, const float* quat) {
+    const int pbytes = 12 * dm.nhum;
+#ifdef GMR_EMULATE
+    in_off = 0;
+    const int head = 0, mid = 0;
+#else
+    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(pos) & 15u);
+    in_off = a >> 2;
+    int head = (int)((16u - a) & 15u);                        // bytes in front of the first 16-byte line boundary
+    if (head > pbytes) head = pbytes;
+    const int mid = (pbytes - head) & ~15;                    // the aligned body
+#endif
+    GMR_LANES
+#ifdef GMR_EMULATE
+      (void)head; (void)mid;
+      if (lane < dm.nhum) {
+        float* dp = s_in() + in_off + 3 * lane; float* dq = s_inq() + 4 * lane;
+        const float* p = pos + 3 * lane; const float* q = quat + 4 * lane;
+        dp[0] = p[0]; dp[1] = p[1]; dp[2] = p[2];
+        dq[0] = q[0]; dq[1] = q[1]; dq[2] = q[2]; dq[3] = q[3];
+      }
+#else
+      const uint32_t dpos = (uint32_t)__cvta_generic_to_shared(s_in() + in_off);
+      if (lane == 0) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_bar());
+        const uint32_t qbytes = 16u * (uint32_t)dm.nhum;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(qbytes + (uint32_t)mid) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(s_inq())), "l"(quat), "r"(qbytes), "r"(bar) : "memory");
+        if (mid > 0)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dpos + (uint32_t)head), "l"(reinterpret_cast<const char*>(pos) + head), "r"((uint32_t)mid), "r"(bar) : "memory");
+      } else if (lane >= 8 && lane < 16) {
+        // head words (lanes 8..10) and tail words (lanes 12..14)
+        const int w = lane - 8;
+        const int nhead = head >> 2, ntail = (pbytes - head - mid) >> 2;
+        int idx = -1;
+        if (w < 4) { if (w < nhead) idx = w; }
+        else if (w - 4 < ntail) idx = ((head + mid) >> 2) + (w - 4);
+        if (idx >= 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dpos + 4u * (uint32_t)idx), "l"(pos + idx) : "memory");
+      }
       asm volatile("cp.async.commit_group;" ::: "memory");
 #endif
     GMR_END
+    in_flight = true;
   }
   GMR_FN void frame_wait() {
+    if (!in_flight) return;
+    in_flight = false;
 #ifndef GMR_EMULATE
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_bar());
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(done) : "r"(bar), "r"(in_phase) : "memory");
+    }
+    in_phase ^= 1u;
     __syncwarp();
 #endif
   }

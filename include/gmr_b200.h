@@ -211,9 +211,12 @@ int gmr_retarget_batch_f64_ex(GmrModel* model, const float* pos, const float* qu
                               int32_t* iters_out, double* err_out, double* targets_out,
                               const GmrBatchExtra* extra, uint32_t flags, void* cuda_stream);
 
-/* Same call with HOST buffers (pinned or pageable): the library chunks the clips, overlaps
- * H2D copies, the solve and D2H copies on its own streams and returns when qpos_out is
- * complete.  This is what a dataset script calls. */
+/* Same call with HOST buffers; returns when every output array is complete.  This is what a dataset script calls.
+ * Page-locked (pinned) arrays are used in place: the kernel pulls each frame's keypoints over the host link one frame
+ * ahead of the solve (TMA bulk copies from the mapped arrays) and writes qpos straight into qpos_out, so the transfer
+ * rides inside the solve and the batch stays one schedule.  Pageable arrays are staged through device scratch with
+ * cudaMemcpyAsync before / after the solve (serial, and in chunks of whole waves only beyond an 8 GB staging budget):
+ * pin the large arrays (pos, quat, qpos_out) for end-to-end throughput.  Each array is treated on its own. */
 int gmr_retarget_batch_host(GmrModel* model, const float* pos, const float* quat, const float* ratio,
                             int32_t C, int32_t T, const float* qpos_init, float* qpos_out,
                             int32_t* iters_out, float* err_out, uint32_t flags);

@@ -18,13 +18,22 @@
 constexpr int NH = 14, NQ = 36;
 
 // one warp per clip, frames in order.  mode 0: 4-byte pos + 16-byte quat cp.async per body (round-1 stage_frame);
-// mode 1: 8-byte chunks of the contiguous pos block + 16-byte chunks of the quat block (coalesced)
+// mode 1: 8-byte chunks of the contiguous pos block + 16-byte chunks of the quat block (coalesced);
+// mode 2: TMA bulk copies (cp.async.bulk, mbarrier completion): the 16-byte aligned body of the pos block (160 B) + an
+//         8-byte cp.async for its head or tail (frames are 168 B apart: odd frames start 8 bytes off), the quat block (224 B)
 template <int DEPTH, int MODE>
 __global__ void __launch_bounds__(512, 1)
 read_kernel(const float* __restrict__ pos, const float* __restrict__ quat, int C, int T, int spin, float* __restrict__ sink) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
   float* ring = reinterpret_cast<float*>(smem) + (size_t)warp * DEPTH * 112;      // per frame: 42 + 56 floats, padded
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)(blockDim.x >> 5) * DEPTH * 112 * 4) + warp * DEPTH;
+  if (MODE == 2) {
+    if (lane == 0) for (int i = 0; i < DEPTH; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bars + i)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+  }
+  uint32_t phase = 0;                                                             // bit i: parity of ring slot i
   float acc = 0.f;
   for (int c = blockIdx.x * wpc + warp; c < C; c += gridDim.x * wpc) {
     const float* p = pos + (size_t)c * T * NH * 3;
@@ -41,6 +50,17 @@ read_kernel(const float* __restrict__ pos, const float* __restrict__ quat, int C
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 12 * lane + 8), "l"(pf + 3 * lane + 2) : "memory");
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 176 + 16 * lane), "l"(qf + 4 * lane) : "memory");
         }
+      } else if (MODE == 2) {
+        const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(pf) & 15u);   // 0 or 8; data lands at dst + off
+        if (lane == 0) {
+          const uint32_t bar = (uint32_t)__cvta_generic_to_shared(bars + (t % DEPTH));
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(160u + 224u) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(d + (off ? 16u : 0u)), "l"(reinterpret_cast<const char*>(pf) + (off ? 8 : 0)), "r"(160u), "r"(bar) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(d + 192u), "l"(qf), "r"(224u), "r"(bar) : "memory");
+        }
+        if (lane == 1) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + (off ? 8u : 160u)), "l"(reinterpret_cast<const char*>(pf) + (off ? 0 : 160)) : "memory");
       } else {
         if (lane < 21) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 8 * lane), "l"(pf + 2 * lane) : "memory");
         if (lane < NH) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 176 + 16 * lane), "l"(qf + 4 * lane) : "memory");
@@ -51,6 +71,12 @@ read_kernel(const float* __restrict__ pos, const float* __restrict__ quat, int C
     for (int t = 0; t < T; t++) {
       if (t + DEPTH - 1 < T) stage(t + DEPTH - 1); else asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+      if (MODE == 2) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(bars + (t % DEPTH)), par = (phase >> (t % DEPTH)) & 1u;
+        uint32_t done = 0;
+        while (!done) asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar), "r"(par) : "memory");
+        phase ^= 1u << (t % DEPTH);
+      }
       __syncwarp();
       const float* src = ring + (t % DEPTH) * 112;
       acc += src[lane] + src[44 + lane];
@@ -131,10 +157,12 @@ int main(int argc, char** argv) {
     for (int rep = 0; rep < 2; rep++) {
       if (with_dma) { CK(cudaEventRecord(f0, s1)); CK(cudaMemcpyAsync(d_pos, h_pos, b_pos, cudaMemcpyHostToDevice, s1)); CK(cudaMemcpyAsync(d_quat, h_quat, b_quat, cudaMemcpyHostToDevice, s1)); CK(cudaEventRecord(f1, s1)); }
       CK(cudaEventRecord(e0, s0));
-      if (depth == 2 && mode == 0) read_kernel<2, 0><<<sms, wpc * 32, smem, s0>>>(p, q, C, T, spin, d_sink);
+      if (mode == 2 && depth == 2) read_kernel<2, 2><<<sms, wpc * 32, smem + wpc * depth * 8, s0>>>(p, q, C, T, spin, d_sink);
+      else if (mode == 2) read_kernel<4, 2><<<sms, wpc * 32, smem + wpc * depth * 8, s0>>>(p, q, C, T, spin, d_sink);
+      else if (depth == 2 && mode == 0) read_kernel<2, 0><<<sms, wpc * 32, smem, s0>>>(p, q, C, T, spin, d_sink);
       else if (depth == 2) read_kernel<2, 1><<<sms, wpc * 32, smem, s0>>>(p, q, C, T, spin, d_sink);
       else if (depth == 4) read_kernel<4, 1><<<sms, wpc * 32, smem, s0>>>(p, q, C, T, spin, d_sink);
-      else read_kernel<8, 1><<<sms, wpc * 32, smem, s0>>>(p, q, C, T, spin, d_sink);
+      else { printf("unsupported depth\n"); return; }
       CK(cudaGetLastError());
       CK(cudaEventRecord(e1, s0)); CK(cudaDeviceSynchronize());
       const float ms = time_ms(e0, e1);
@@ -146,12 +174,15 @@ int main(int argc, char** argv) {
   run_read("read_hbm", 2, 1, d_pos, d_quat, 0, false);
   run_read("read_zero_copy", 2, 0, m_pos, m_quat, 0, false);
   run_read("read_zero_copy", 2, 1, m_pos, m_quat, 0, false);
+  run_read("read_zero_copy", 2, 2, m_pos, m_quat, 0, false);
+  run_read("read_hbm", 2, 2, d_pos, d_quat, 0, false);
+  run_read("read_zero_copy", 4, 2, m_pos, m_quat, 0, false);
   run_read("read_zero_copy", 4, 1, m_pos, m_quat, 0, false);
-  run_read("read_zero_copy", 8, 1, m_pos, m_quat, 0, false);
   // with a stand-in for the solve (~80 ms of ALU time per batch when data is free): does the link keep up?
   run_read("read_hbm_paced", 2, 1, d_pos, d_quat, 6000, false);
   run_read("read_zero_copy_paced", 2, 1, m_pos, m_quat, 6000, false);
   run_read("read_zero_copy_paced", 4, 1, m_pos, m_quat, 6000, false);
+  run_read("read_zero_copy_paced", 2, 2, m_pos, m_quat, 6000, false);
   run_read("read_zero_copy_with_dma", 4, 1, m_pos, m_quat, 0, true);
 
   for (int rep = 0; rep < 2; rep++) {
