@@ -187,5 +187,5 @@ EXPORTED_SYMBOLS = [
     "gmr_retarget_batch_host", "gmr_retarget_batch_host_ex", "gmr_launch_count", "gmr_last_error", "gmr_kernel_info",
     "gmr_retarget_batch_ex", "gmr_retarget_batch_f64_ex", "gmr_finalize_motion",
     "gmr_stream_create", "gmr_stream_destroy", "gmr_stream_reset", "gmr_stream_retarget",
-    "gmr_produce_bvh_frames", "gmr_produce_smplx_frames", "gmr_retarget_multi",
+    "gmr_produce_bvh_frames", "gmr_produce_smplx_frames", "gmr_retarget_multi", "gmr_debug_trace",
 ]

@@ -30,6 +30,7 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<int64_t> g_launches{0};
+std::atomic<long long*> g_trace{nullptr};      // gmr_debug_trace
 
 int set_err(int code, const std::string& msg) { g_err = msg; return code; }
 int cuda_err(cudaError_t e, const char* what) {
@@ -94,23 +95,55 @@ gmr_order_kernel(const GmrConsts<R>* __restrict__ mc, const float* __restrict__ 
   else order[C + atomicAdd(&counts[1], 1)] = c;
 }
 
-// Second scheduling hint, for batches of one to a few waves: after frame 0 (solved for every clip by a first
-// launch) a clip that will be slow is recognisable — its task error stays above 1 where a converged clip is at
-// ~0.07.  Same list layout as above: order[0 .. n_slow) slow, order[C .. C + n_normal) the rest.
+// ---- clip scheduler of the scheduled launch (gmr_retarget_kernel, part_w > 0) ---------------------------------------
+// Two FIFO rings of clip ids in global memory: ring entries are 64-bit {ticket + 1, clip}; the slow ring occupies
+// ring[0 .. cap), the normal ring ring[cap .. 2 cap).  gmr_classify_kernel fills the first n_slow0 / n_norm0 tickets, then the
+// warps push and pop.  Every operation is a handful of independent atomics (no compare-and-swap loop, no ordered publish):
+//   push: ticket = res++ ; ring[ticket % cap] = {ticket + 1, clip} ; avail++
+//   pop : if (avail-- <= 0) { avail++ ; empty } else { ticket = head++ ; wait until ring[ticket % cap].ticket == ticket + 1 }
+// (`avail` counts published entries, so a claimed ticket's entry is at most a few instructions away.)  A clip is in at most one
+// ring at a time, so a ring never holds more than C entries; with cap = 2 C + 2 an entry could only be overwritten before its
+// claimant reads it if C + 1 further tickets were claimed in between.
+enum { SQ_AVAIL_N = 0, SQ_NSLOW0 = 1, SQ_NNORM0 = 2, SQ_AVAIL_S = 3, SQ_RES_N = 4, SQ_HEAD_N = 5, SQ_RES_S = 6, SQ_HEAD_S = 7,
+       SQ_DONE = 8, SQ_IDLE_STEAL = 9, SQ_INTS = 16 };
+__device__ __forceinline__ int ldv(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ int sq_pop(int* q, const long long* ring, int cap, int avail_i, int head_i, int n0) {
+  if (n0 + ldv(q + avail_i) <= 0) return -1;                          // cheap look before touching the counter
+  if (n0 + atomicSub(q + avail_i, 1) <= 0) { atomicAdd(q + avail_i, 1); return -1; }
+  const int t = atomicAdd(q + head_i, 1);
+  const volatile long long* e = ring + t % cap;
+  long long v;
+  while ((int)((v = *e) >> 32) != t + 1) { }
+  __threadfence();                                                    // the clip's state was written before the entry
+  return (int)(v & 0xffffffffll);
+}
+__device__ __forceinline__ void sq_push(int* q, long long* ring, int cap, int avail_i, int res_i, int n0, int c) {
+  const int t = n0 + atomicAdd(q + res_i, 1);
+  __threadfence();
+  *reinterpret_cast<volatile long long*>(ring + t % cap) = ((long long)(t + 1) << 32) | (long long)(unsigned)c;
+  __threadfence();
+  atomicAdd(q + avail_i, 1);
+}
+
+// After frame 0 (solved for every clip by a first launch) a clip that will be slow is recognisable: its task error stays
+// above 1 where a converged clip is at ~0.07-0.1 (from frame 1 on ANY threshold between 0.3 and 1.9 splits the benchmark
+// clips identically; after frame 0 a quarter of the suspects still converge within a few frames and are handed back by the
+// scheduler).  Fills the two rings of the scheduled launch.
 __global__ void __launch_bounds__(256)
-gmr_classify_kernel(const double* __restrict__ state, int stride, int nq, int C, double thresh,
-                    int* __restrict__ counts, int* __restrict__ order) {
+gmr_classify_kernel(const double* __restrict__ state, int stride, int nq, int C, int cap, double thresh,
+                    int* __restrict__ counts, long long* __restrict__ ring) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  if (state[(size_t)c * stride + nq + 1] > thresh) order[atomicAdd(&counts[0], 1)] = c;
-  else order[C + atomicAdd(&counts[1], 1)] = c;
+  if (state[(size_t)c * stride + nq + 1] > thresh) { const int t = atomicAdd(&counts[0], 1); ring[t] = ((long long)(t + 1) << 32) | c; }
+  else { const int t = atomicAdd(&counts[1], 1); ring[cap + t] = ((long long)(t + 1) << 32) | c; }
 }
 
 template <typename R, typename IO, int MAXWARPS>
 __global__ void __launch_bounds__(MAXWARPS * 32, 1)
 gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ GmrScal<R> ks,
                     const GmrConsts<R>* __restrict__ gconsts, const __grid_constant__ GmrIO<IO> io, uint32_t kflags,
-                    int* __restrict__ queue, const int* __restrict__ order, int part_w, int part_pct) {
+                    int* __restrict__ queue, const int* __restrict__ order, long long* __restrict__ rings, int part_w, int part_pct,
+                    int seg_frames, double slow_err) {
   extern __shared__ __align__(128) unsigned char gmr_dyn_smem[];
   unsigned char* const smem = gmr_dyn_smem;
   constexpr int CB = consts_bytes<R>();
@@ -129,49 +162,114 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
     if (threadIdx.x == 0) *ws.cta_active = wpc;
     __syncthreads();
   }
-  // Clips come from a global queue (one atomic per clip): clips differ several-fold in the number of
-  // IK steps they need, so a warp that finishes early takes the next clip instead of idling behind a
-  // static assignment.  The first gridDim * wpc clips are handed out without touching the queue.
-  const int nw = gridDim.x * wpc;
-  const int n_hard = order ? queue[1] : 0;                            // queue = {next position, n_hard, n_easy, next slow position}
-  // Partitioned mode (part_w > 0, slow clips known): a few SMs serve the slow list with only `pw` warps each, so
-  // that the longest sequential chains run at nearly the speed of a lone warp instead of sharing their SM's issue
-  // slots with 15-27 other clips; every other SM serves the normal list at full occupancy.  A warp whose list is
-  // empty helps with the other one.  Throughput is traded for the length of the batch's critical path.
-  const int n_norm = part_w > 0 ? queue[2] : 0;
-  bool slow_block = false, idle = false;
+  // ONE loop and one inlined copy of the solver (two call sites would double the kernel's code, which already exceeds
+  // the instruction cache), serving both kinds of launch:
+  //
+  // Plain launch (part_w == 0): clips come from a global queue (one atomic per clip) - clips differ several-fold in the
+  // number of IK steps they need, so a warp that finishes early takes the next clip instead of idling behind a static
+  // assignment.  The first gridDim * wpc clips are handed out without touching the queue; with `order`
+  // (gmr_order_kernel) the hard clips come first.
+  //
+  // Scheduled launch (part_w > 0; every clip already has a state: frame 0 was solved by a first launch and
+  // gmr_classify_kernel split the clips by the task error it left).  Clips advance in SEGMENTS of seg_frames frames; between
+  // segments a clip lives in its state record and in one of two FIFO rings:
+  //   * slow clips (error still above slow_err after the last frame: stuck in a local minimum with joints on their limits,
+  //     2-3x the IK steps of a normal clip and ~1.7 factorisations per step - they are the batch's critical path) run on
+  //     "sparse" SMs, part_w warps per SM (2 per scheduler: ~13 % slower than a lone warp instead of ~60 % on a full SM),
+  //     and keep their warp from segment to segment;
+  //   * normal clips go round robin through the other ("dense", fully occupied) SMs: after every segment a clip goes to
+  //     the back of the ring while others are waiting, so all of them finish within one segment of each other instead of
+  //     in whole-clip waves;
+  //   * a clip changes class when its error crosses slow_err (false suspects leave the sparse SMs after one segment);
+  //   * when the normal ring runs dry, warps 0-3 of the dense SMs (one per scheduler) take slow clips, and slow clips on
+  //     sparse SMs hand themselves over at their next segment boundary: the tail of the batch runs at lone-warp speed.
+  // Pure scheduling: a clip's frames are solved in order from its own state, whichever warps run its segments.
+  // Nothing of the scheduler stays in registers across a segment (the solver needs all of them): the warp's role, what it
+  // is running and the clip id live in two spare words next to the warp's mbarrier and are re-read between segments.
+  enum { W_SLOW_BLOCK = 1, W_STEALER = 2, W_TOOK_SLOW = 4, W_COUNTED_IDLE = 8, W_HAVE = 16 };
+  volatile int* const wword = reinterpret_cast<volatile int*>(reinterpret_cast<unsigned char*>(ws.s_bar()) + 8);   // [0] role bits, [1] clip
   if (part_w > 0) {
+    const int n_s0 = queue[SQ_NSLOW0];
     int pw = part_w;
-    const int max_blocks = (int)gridDim.x * part_pct / 100;           // at most this share of the SMs
-    if (max_blocks > 0 && (n_hard + pw - 1) / pw > max_blocks) pw = (n_hard + max_blocks - 1) / max_blocks;
+    const int max_blocks = (int)gridDim.x * part_pct / 100;           // at most this share of the SMs goes sparse
+    if (max_blocks > 0 && (n_s0 + pw - 1) / pw > max_blocks) pw = (n_s0 + max_blocks - 1) / max_blocks;
     if (pw > wpc) pw = wpc;
-    const int b_slow = (n_hard + pw - 1) / pw < max_blocks ? (n_hard + pw - 1) / pw : max_blocks;
-    slow_block = (int)blockIdx.x < b_slow;
-    idle = slow_block && warp >= pw;
+    const int b_slow = (n_s0 + pw - 1) / pw < max_blocks ? (n_s0 + pw - 1) / pw : max_blocks;
+    const bool slow_block = (int)blockIdx.x < b_slow;
+    if (slow_block && warp >= pw) return;                              // the sparse SMs' spare warps
+    if (lane == 0) wword[0] = slow_block ? W_SLOW_BLOCK : (warp < 4 ? W_STEALER : 0);
+    __syncwarp();
   }
-  // one loop, one inlined copy of the solver: the first clip of a warp is its static slot (plain mode) or comes
-  // from the queues (partitioned mode)
-  int p = part_w > 0 ? -1 : warp * (int)gridDim.x + (int)blockIdx.x;
+  int p = warp * (int)gridDim.x + (int)blockIdx.x;                    // plain launch: position in the clip order
   for (;;) {
     int c = -1;
-    if (part_w > 0) {
-      if (idle) break;
+    if (part_w == 0) {
+      if (p >= C) break;
+      const int n_hard = order ? queue[1] : 0;                        // queue = {next position, n_hard, n_easy, -}
+      c = order ? (p < n_hard ? order[p] : order[C + p - n_hard]) : p;
+    } else {
       if (lane == 0) {
-        if (slow_block) { const int i = atomicAdd(&queue[3], 1); if (i < n_hard) c = order[i]; }
-        if (c < 0) { const int i = atomicAdd(&queue[0], 1); if (i < n_norm) c = order[C + i]; }
-        if (c < 0 && !slow_block) { const int i = atomicAdd(&queue[3], 1); if (i < n_hard) c = order[i]; }
+        int w = wword[0];
+        if (w & W_HAVE) c = wword[1];                                  // the clip keeps its warp for another segment
+        else {
+          const int cap = 2 * C + 2;
+          const int n_s0 = queue[SQ_NSLOW0], n_n0 = queue[SQ_NNORM0];
+          w &= ~W_TOOK_SLOW;
+          if (w & W_SLOW_BLOCK) { c = sq_pop(queue, rings, cap, SQ_AVAIL_S, SQ_HEAD_S, n_s0); if (c >= 0) w |= W_TOOK_SLOW; }
+          if (c < 0) c = sq_pop(queue, rings + cap, cap, SQ_AVAIL_N, SQ_HEAD_N, n_n0);
+          if (c < 0 && (w & W_STEALER)) { c = sq_pop(queue, rings, cap, SQ_AVAIL_S, SQ_HEAD_S, n_s0); if (c >= 0) w |= W_TOOK_SLOW; }
+          if (c < 0) {
+            if (ldv(queue + SQ_DONE) >= C) c = -2;
+            else if ((w & W_STEALER) && !(w & W_COUNTED_IDLE)) { atomicAdd(queue + SQ_IDLE_STEAL, 1); w |= W_COUNTED_IDLE; }
+          } else {
+            if (w & W_COUNTED_IDLE) { atomicSub(queue + SQ_IDLE_STEAL, 1); w &= ~W_COUNTED_IDLE; }
+            w |= W_HAVE;
+          }
+          wword[0] = w; wword[1] = c;
+        }
       }
       c = __shfl_sync(0xffffffffu, c, 0);
-    } else {
-      if (p < C) c = order ? (p < n_hard ? order[p] : order[C + p - n_hard]) : p;
+      if (c == -2) break;
+      if (c < 0) { __nanosleep(1000); continue; }
+      __threadfence();                                                 // the clip's state may have been written by another warp
     }
-    if (c < 0) break;
-    ws.template run_clip<IO>(io, c);
+    const int nt = ws.template run_clip<IO>(io, c, part_w > 0 ? seg_frames : 0);
     if (part_w == 0) {
       int nxt = 0;
-      if (lane == 0) nxt = nw + atomicAdd(queue, 1);
+      if (lane == 0) nxt = gridDim.x * wpc + atomicAdd(queue, 1);
       p = __shfl_sync(0xffffffffu, nxt, 0);
+      continue;
     }
+    // scheduled launch: what happens to the clip after this segment
+    __threadfence();                                                   // its state record, before anything is published
+    __syncwarp();
+    int act = 0;                                                       // 1: back off after handing a slow clip over
+    if (lane == 0) {
+      const int cc = wword[1];
+      int w = wword[0];
+      int T_c = io.T;
+      if (io.ex.lengths) { T_c = io.ex.lengths[cc]; T_c = T_c < 0 ? 0 : (T_c > io.T ? io.T : T_c); }
+      if (nt < 0 || nt >= T_c) {                                       // complete (or stopped by a fatal status)
+        atomicAdd(queue + SQ_DONE, 1);
+        w &= ~W_HAVE;
+      } else {
+        // a slow clip keeps its warp, unless it sits on a sparse SM while lone-speed slots are idle elsewhere; a normal
+        // clip keeps its warp while nobody is waiting in the normal ring
+        const bool now_slow = (double)ws.s_piv()[1] > slow_err, took_slow = (w & W_TOOK_SLOW) != 0;
+        bool keep;
+        if (now_slow) keep = took_slow && !((w & W_SLOW_BLOCK) && ldv(queue + SQ_IDLE_STEAL) > 0);
+        else keep = !took_slow && queue[SQ_NNORM0] + ldv(queue + SQ_AVAIL_N) <= 0;
+        if (!keep) {
+          const int cap = 2 * C + 2;
+          if (now_slow) sq_push(queue, rings, cap, SQ_AVAIL_S, SQ_RES_S, queue[SQ_NSLOW0], cc);
+          else sq_push(queue, rings + cap, cap, SQ_AVAIL_N, SQ_RES_N, queue[SQ_NNORM0], cc);
+          w &= ~W_HAVE;
+          act = now_slow && took_slow;
+        }
+      }
+      wword[0] = w;
+    }
+    if (__shfl_sync(0xffffffffu, act, 0)) __nanosleep(4000);           // let the idle lone-speed slot win the pop
   }
   ws.convoy_retire();
 }
@@ -362,7 +460,7 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
   flags = (flags & 0xffffu) | (convoy ? GMR_FLAG_INTERNAL_CONVOY : 0u);
   GmrIO<IO> io{};
   io.pos = pos; io.quat = quat; io.ratio = ratio; io.qinit = qinit; io.qout = qout; io.iters = iters; io.err = err; io.tg = tg;
-  io.C = C; io.T = T; io.flags = flags & 0xffffu; io.ex = ex;
+  io.C = C; io.T = T; io.flags = flags & 0xffffu; io.ex = ex; io.trace = g_trace.load();
   const GmrDims& dims = sizeof(R) == 4 ? m->dims32 : m->dims64;
   const int slots = grid * wpc;
   static const int lpt_env = getenv("GMR_LPT") ? atoi(getenv("GMR_LPT")) : 1;
@@ -370,33 +468,39 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
   // (tools/prof/mix_case.py, ~10 % of the clips classified slow).  float32: 4 warps / 55 % (64 ms vs 70 ms at 40 %,
   // worse beyond 65 %).  float64 has 16 instead of 28 warps per SM to give away, so sparse slow SMs cost it more
   // capacity: 6 warps / 45 % (82 ms vs 86 ms at 4 / 55 % and 88-90 ms at 8-10 warps / 30-35 %).
-  static const int part_env = getenv("GMR_PARTITION") ? atoi(getenv("GMR_PARTITION")) : (sizeof(R) == 8 ? 6 : 4);
+  static const int part_env = getenv("GMR_PARTITION") ? atoi(getenv("GMR_PARTITION")) : 8;
 
-  // ---- batches of ~1-4 waves: frame 0 for every clip, classify, then the rest with slow clips on their own SMs ----
-  const bool two_phase = part_env > 0 && !own_queue && !convoy && !(flags & GMR_FLAG_NO_SOLVE) && T >= 16 &&
-                         C > 2 * m->num_sms * part_env && C <= 4 * m->num_sms * max_warps<R>();
+  // ---- more clips than the sparse part could hold: frame 0 for every clip, classify, then the scheduled launch ----
+  // (see gmr_retarget_kernel).  pw = warps per sparse SM: 2 per scheduler keeps a slow clip within ~13 % of the speed of a
+  // lone warp (tools/prof/slow_curve.py: 21.5 / 24.4 / 27.9 / 34.3 us per IK step at 1-4 / 8 / 10 / 16 warps per SM) at
+  // twice the capacity of 1 per scheduler; the number of sparse SMs follows from the number of suspects.  Segment
+  // length: 25 frames = 2-3 ms per visit, thousands of IK steps per ring operation.
+  static const int seg_env = getenv("GMR_SEGMENT") ? atoi(getenv("GMR_SEGMENT")) : 25;
+  static const double slow_err_env = getenv("GMR_SLOW_ERR") ? atof(getenv("GMR_SLOW_ERR")) : 1.0;
+  const bool two_phase = part_env > 0 && seg_env > 0 && !own_queue && !convoy && !(flags & GMR_FLAG_NO_SOLVE) && T >= 16 &&
+                         C > 2 * m->num_sms * part_env;
   if (two_phase) {
-    const int stride = gmr_state_stride(dims.nq);
-    const size_t b_state = ((size_t)C * stride * sizeof(double) + 255) & ~(size_t)255, b_order = (size_t)2 * C * sizeof(int);
+    const int stride = gmr_state_stride(dims.nq), cap = 2 * C + 2;
+    const size_t b_state = ((size_t)C * stride * sizeof(double) + 255) & ~(size_t)255, b_ring = (size_t)2 * cap * sizeof(long long);
     StreamScratch scratch(m->pool, st);                      // freed in stream order on every exit path
-    CK(scratch.alloc(256 + b_state + b_order));              // [ two clip queues | state | lists ]
+    CK(scratch.alloc(256 + b_state + b_ring));               // [ launch A's clip queue, the scheduler's counters | state | rings ]
     int* q1 = reinterpret_cast<int*>(scratch.p);
-    int* q2 = q1 + 4;
+    int* q2 = q1 + 16;
     double* state = reinterpret_cast<double*>(scratch.p + 256);
-    int* order2 = reinterpret_cast<int*>(scratch.p + 256 + b_state);
-    CK(cudaMemsetAsync(q1, 0, 8 * sizeof(int), st));
+    long long* rings = reinterpret_cast<long long*>(scratch.p + 256 + b_state);
+    CK(cudaMemsetAsync(q1, 0, 256, st));
     // launch A: frame 0 of every clip (balanced work: every clip starts from the same configuration)
     GmrIO<IO> ioa = io;
     ioa.t_begin = 0; ioa.t_end = 1; ioa.state = state;
-    kern<<<grid, wpc * 32, smem, st>>>(dims, scal_of<R>(m), dc, ioa, flags, q1, (const int*)nullptr, 0, 0);
+    kern<<<grid, wpc * 32, smem, st>>>(dims, scal_of<R>(m), dc, ioa, flags, q1, (const int*)nullptr, (long long*)nullptr, 0, 0, 0, 0.0);
     CK(cudaGetLastError());
-    gmr_classify_kernel<<<(C + 255) / 256, 256, 0, st>>>(state, stride, dims.nq, C, 1.0, q2 + 1, order2);
+    gmr_classify_kernel<<<(C + 255) / 256, 256, 0, st>>>(state, stride, dims.nq, C, cap, slow_err_env, q2 + SQ_NSLOW0, rings);
     CK(cudaGetLastError());
-    // launch B: frames 1 .. T-1, partitioned
+    // launch B: frames 1 .. T-1, scheduled
     GmrIO<IO> iob = io;
     iob.t_begin = 1; iob.t_end = 0; iob.state = state;
-    static const int pct_env = getenv("GMR_PARTITION_PCT") ? atoi(getenv("GMR_PARTITION_PCT")) : (sizeof(R) == 8 ? 45 : 55);
-    kern<<<grid, wpc * 32, smem, st>>>(dims, scal_of<R>(m), dc, iob, flags, q2, order2, part_env, pct_env);
+    static const int pct_env = getenv("GMR_PARTITION_PCT") ? atoi(getenv("GMR_PARTITION_PCT")) : 50;
+    kern<<<grid, wpc * 32, smem, st>>>(dims, scal_of<R>(m), dc, iob, flags, q2, (const int*)nullptr, rings, part_env, pct_env, seg_env, slow_err_env);
     CK(cudaGetLastError());
     g_launches.fetch_add(3);
     return GMR_OK;
@@ -415,7 +519,7 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
     g_launches.fetch_add(1);
     CK(cudaGetLastError());
   }
-  kern<<<grid, wpc * 32, smem, st>>>(dims, scal_of<R>(m), dc, io, flags, queue, order, 0, 0);
+  kern<<<grid, wpc * 32, smem, st>>>(dims, scal_of<R>(m), dc, io, flags, queue, order, (long long*)nullptr, 0, 0, 0, 0.0);
   g_launches.fetch_add(1);
   CK(cudaGetLastError());
   return GMR_OK;
@@ -957,6 +1061,10 @@ int gmr_produce_smplx_frames(const float* global_orient, const float* full_pose,
 }
 
 int64_t gmr_launch_count(void) { return g_launches.load(); }
+
+// Profiling aid, not part of the documented ABI: while a device buffer of [2C,4] int64 is registered, every clip of a
+// single-robot launch records {start ns, end ns, SM | warp << 16, solves | factorisations << 32} (tools/prof/timeline.py).
+void gmr_debug_trace(long long* device_buffer) { g_trace.store(device_buffer); }
 
 const char* gmr_last_error(void) { return g_err.c_str(); }
 

@@ -227,6 +227,13 @@ template <> __device__ __forceinline__ float g_atan2<float>(float y, float x) { 
 template <> __device__ __forceinline__ float g_abs<float>(float x) { return fabsf(x); }
 #endif
 
+// global load that bypasses the (non-coherent) L1: clip state records and status words travel between SMs within one launch
+#ifdef GMR_EMULATE
+template <typename T> GMR_FN T g_ldcg(const T* p) { return *p; }
+#else
+template <typename T> GMR_FN T g_ldcg(const T* p) { return __ldcg(p); }
+#endif
+
 // 4 consecutive elements from 16-byte aligned shared memory (one LDS.128 / two LDS.128)
 GMR_FN void g_ld4(const float* p, float* v) {
 #ifdef GMR_EMULATE
@@ -336,12 +343,15 @@ template <typename IO> struct GmrIO {
   int32_t C, T; uint32_t flags, _pad;
   GmrBatchExtra ex;
   // a launch may cover only frames [t_begin, t_end) of every clip (t_end <= 0: to the end); `state`
-  // ([C, nq + 4] doubles: qpos | running lowest z | last error | working sets as 4 x u32) carries a clip from
-  // one launch to the next at full precision
+  // ([C, nq + 6] doubles: qpos | running lowest z | last error | working sets as 4 x u32 | next frame | pad) carries a
+  // clip from one launch - or one SEGMENT of the scheduled launch, see run_clip - to the next at full precision
   int32_t t_begin, t_end;
   double* state;
+  // profiling aid (gmr_debug_trace): [2C,4] int64 {start ns, end ns, sm | warp << 16, factorisations} per clip;
+  // rows [0, C) are written by launches that start at frame 0, rows [C, 2C) by launches that continue a clip
+  long long* trace;
 };
-GMR_HD constexpr int gmr_state_stride(int nq) { return nq + 4; }
+GMR_HD constexpr int gmr_state_stride(int nq) { return nq + 6; }
 
 // =============================================================================================
 template <typename R>
@@ -1359,33 +1369,51 @@ struct WarpSolver {
   //   ex.local_body_pos [C,T,nb,3]  FK with an identity root = R_root^T (x_b - x_root), and
   //   ex.lowest_z [C]               min over frames and bodies of the world z (the height adjustment of :118-123)
   // cost one pass over the body poses already in shared memory.
+  // seg_frames > 0 (scheduled launch): run at most that many frames starting at the frame recorded in the clip's state,
+  // save the state again and return the next frame to run (== the clip's length when it is complete, -1 when the clip
+  // was stopped by a fatal status); the task error of the last frame solved (the scheduler's slow / normal signal)
+  // is left in s_piv()[1].  seg_frames == 0: the launch's own frame range [t_begin, t_end).
   template <typename IO>
-  GMR_FN void run_clip(const GmrIO<IO>& io, int c) {
+  GMR_FN int run_clip(const GmrIO<IO>& io, int c, int seg_frames = 0) {
     const uint32_t flags = io.flags;
     const size_t f0 = (size_t)c * io.T;
     int T = io.T;
     if (io.ex.lengths) { T = io.ex.lengths[c]; T = T < 0 ? 0 : (T > io.T ? io.T : T); }     // ragged batch: this clip's own length
     const float* const pos = io.pos + f0 * dm.nhum * 3;
     const float* const quat = io.quat + f0 * dm.nhum * 4;
-    const int tb = io.t_begin;
-    if (io.t_end > 0 && io.t_end < T) T = io.t_end;
-    if (tb >= T) return;                                              // nothing of this clip in this launch's frame range
+    int tb = io.t_begin;
+    if (seg_frames > 0) {
+      tb = (int)g_ldcg(io.state + (size_t)c * gmr_state_stride(dm.nq) + dm.nq + 4);
+      if (tb + seg_frames < T) T = tb + seg_frames;
+    } else if (io.t_end > 0 && io.t_end < T) T = io.t_end;
+    if (tb >= T) return tb;                                           // nothing of this clip in this launch's frame range
     const bool resume = tb > 0 && io.state;
     stat_flags = 0;
+    stat_refactor = 0;
+#ifndef GMR_EMULATE
+    if (io.trace && lane_ == 0) {                                     // nothing of the trace stays live across the clip
+      long long* o = io.trace + 4 * ((size_t)(tb > 0 ? io.C : 0) + c);
+      if (seg_frames == 0 || g_ldcg(o) == 0) { long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0)); o[0] = t0; o[3] = 0; }
+    }
+#endif
     int stat_frame = -1;                                              // frame of the first status event
     {
     const double* const st = io.state ? io.state + (size_t)c * gmr_state_stride(dm.nq) : nullptr;   // not kept live: re-derived at the end
-    if (resume && !(st[dm.nq + 1] == st[dm.nq + 1])) return;          // the clip was stopped in an earlier launch (error = NaN)
-    if (resume) set_qpos(st);
+    if (resume) { const double e = g_ldcg(st + dm.nq + 1); if (!(e == e)) return -1; }   // the clip was stopped earlier (error = NaN)
+    if (resume) {
+      GMR_LANES
+        for (int i = lane; i < dm.nq; i += 32) s_q()[i] = R(g_ldcg(st + i));
+      GMR_END
+    }
     else if (io.qinit) set_qpos(io.qinit + (size_t)c * dm.nq);
     else set_qpos(mc.qpos0);
     warm_lo0 = warm_lo1 = warm_hi0 = warm_hi1 = 0;
     {
       const uint32_t* w = resume ? reinterpret_cast<const uint32_t*>(st + dm.nq + 2) : (io.ex.warm_state ? io.ex.warm_state + 4 * c : nullptr);
-      if (w) { warm_lo0 = w[0]; warm_hi0 = w[1]; warm_lo1 = w[2]; warm_hi1 = w[3]; }
+      if (w) { warm_lo0 = g_ldcg(w); warm_hi0 = g_ldcg(w + 1); warm_lo1 = g_ldcg(w + 2); warm_hi1 = g_ldcg(w + 3); }
     }
     GMR_LANES
-      if (lane == 0) { s_piv()[0] = io.ratio ? R(io.ratio[c]) : R(1); s_piv()[3] = resume ? R(st[dm.nq]) : R(INFINITY); }   // height ratio, running lowest z
+      if (lane == 0) { s_piv()[0] = io.ratio ? R(io.ratio[c]) : R(1); s_piv()[3] = resume ? R(g_ldcg(st + dm.nq)) : R(INFINITY); }   // height ratio, running lowest z
     GMR_END
     }
     stage_frame(pos + (size_t)tb * dm.nhum * 3, quat + (size_t)tb * dm.nhum * 4);
@@ -1497,11 +1525,21 @@ struct WarpSolver {
         frame_start = true;
       }
     }
+#ifndef GMR_EMULATE
+    if (io.trace && lane_ == 0) {
+      long long t1; unsigned smid;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      long long* o = io.trace + 4 * ((size_t)(io.t_begin > 0 ? io.C : 0) + c);
+      o[1] = t1; o[2] = (long long)(smid | ((threadIdx.x >> 5) << 16));
+      o[3] = g_ldcg(o + 3) + (long long)stat_refactor;                   // segments of one clip accumulate into one row
+    }
+#endif
     const bool stopped = (stat_flags & GMR_STATUS_FATAL) != 0;
     if (io.ex.status && stat_flags) {
       GMR_LANES
         if (lane == 0) {
-          const int32_t old = io.ex.status[c];
+          const int32_t old = g_ldcg(io.ex.status + c);
           io.ex.status[c] = old ? (old | (int32_t)stat_flags) : (int32_t)(stat_flags | ((uint32_t)stat_frame << 8));
         }
       GMR_END
@@ -1515,6 +1553,7 @@ struct WarpSolver {
           st[dm.nq + 1] = stopped ? (double)NAN : (double)(dm.use2 ? e1 : e0);
           uint32_t* w = reinterpret_cast<uint32_t*>(st + dm.nq + 2);
           w[0] = warm_lo0; w[1] = warm_hi0; w[2] = warm_lo1; w[3] = warm_hi1;
+          st[dm.nq + 4] = (double)t;
         }
       GMR_END
     }
@@ -1526,5 +1565,11 @@ struct WarpSolver {
         }
       GMR_END
     }
+    if (seg_frames > 0) {
+      GMR_LANES
+        if (lane == 0) s_piv()[1] = dm.use2 ? e1 : e0;
+      GMR_END
+    }
+    return stopped ? -1 : t;                                          // next frame to run (>= the clip's length: complete)
   }
 };

@@ -228,6 +228,10 @@ int gmr_retarget_batch_host_ex(GmrModel* model, const float* pos, const float* q
 
 /* number of kernel launches issued by this library since load (for bench bookkeeping) */
 int64_t gmr_launch_count(void);
+/* profiling aid: while a device buffer of [2C,4] int64 is registered (NULL to stop), every clip of a single-robot launch
+ * records {start ns, end ns, SM | warp << 16, IK steps | factorisations << 32}; rows [0,C) by launches that start at
+ * frame 0, rows [C,2C) by launches that continue a clip (tools/prof/timeline.py) */
+void gmr_debug_trace(long long* device_buffer);
 const char* gmr_last_error(void);
 /* static properties of the solve kernel for (model, C): for reports */
 int gmr_kernel_info(GmrModel* model, int32_t precision_bits, int32_t* threads_per_cta,
