@@ -41,8 +41,22 @@ def parse_args():
     ap.add_argument("--src", default="smplx")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-f32", action="store_true", help="skip the float32 fast-mode side measurement")
-    return ap.parse_args()
+    ap.add_argument("--no-f32", action="store_true", help="skip the float32 (approximate mode) side measurement")
+    ap.add_argument("--config", type=int, default=1, choices=[0, 1, 2, 3, 4],
+                    help="BASELINE.json configs[K]: 0 single-clip trace, 1 G1 4096 clips (headline, default), 2 booster_t1/bvh 8192, "
+                         "3 hightorque_hi 8192, 4 mixed-robot 65536 clips sharded over the GPUs (strong scaling)")
+    ap.add_argument("--workload", default=None, choices=[None, "mixed"], help="alias: --workload mixed == --config 4")
+    ap.add_argument("--shard", default="lpt", choices=["lpt", "contiguous"], help="how clips are assigned to ranks")
+    a = ap.parse_args()
+    if a.workload == "mixed":
+        a.config = 4
+    explicit = {x.split("=")[0] for x in sys.argv[1:] if x.startswith("--")}
+    preset = {0: dict(robot="unitree_g1", src="smplx", clips=1), 2: dict(robot="booster_t1", src="bvh", clips=8192),
+              3: dict(robot="hightorque_hi", src="smplx", clips=8192), 4: dict(clips=65536)}.get(a.config, {})
+    for k, v in preset.items():
+        if "--" + k not in explicit:
+            setattr(a, k, v)
+    return a
 
 
 # ---- algorithmic work (dense convention; the figure roofline.achieved uses) ----
@@ -136,8 +150,10 @@ def workload_config(args, table):
     C, T = args.clips, args.frames
     in_mb = C * T * table.nh * 7 * 4 / 1e6
     return {"workload": f"{args.robot} ({args.src} mapping), {C} synthetic clips x {T} frames per GPU, "
-                        "sequential two-stage IK warm-started per clip (BASELINE.json configs[1])",
-            "clips_per_gpu": C, "frames": T, "sharding": "clips, contiguous ranges per rank, no collective",
+                        f"sequential two-stage IK warm-started per clip (BASELINE.json configs[{args.config}])",
+            "clips_per_gpu": C, "frames": T,
+            "sharding": ("clips dealt to the ranks by a hardness proxy (sharding.lpt_shard), " if args.shard == "lpt" else
+                         "clips, contiguous ranges per rank, ") + "no collective on the solve path",
             "l2": f"inputs ~{in_mb:.0f} MB per step {'>' if in_mb > 126 else '<= (reduced-size run: L2 not flushed)'} 126 MB L2"}
 
 
@@ -159,51 +175,331 @@ def cpu_reference_run(robot, table, clips, nthreads=0, src=None, robot_name=None
 
 
 def main_reference(args):
-    """CPU arm on the SAME workload as the GPU arm (same generator, robot, clip ids 0..C-1, T).  One step = one pass over a
+    """CPU arm on the SAME workload as the GPU arm (same generator, robots, clip ids, T).  One step = one pass over a
     bounded, rotating sample of those clips (step k takes the next `sample` clip ids, wrapping around), sized from a
     short probe so that warm-up + K steps take about two minutes whatever the host and whichever implementation runs."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from general_motion_retargeting_b200 import params
+    from general_motion_retargeting_b200.ik_config import compile_task_table
     from general_motion_retargeting_b200.synthetic import make_clips
-    robot, table = load_problem(args)
     cores = os.cpu_count() or 1
     C, T = args.clips, args.frames
+    if args.config == 4:         # clip i -> robot i mod 5
+        probs = []
+        for k, name in enumerate(MIXED_ROBOTS):
+            robot, cfg, _ = params.load_pack("smplx", name)
+            probs.append(("smplx", name, robot, compile_task_table(robot, cfg), k, len(MIXED_ROBOTS)))
+        config, metric = mixed_config(args), "retargeted frames/sec (mixed robots: g1/t1/toddy/n1/pm01)"
+    else:
+        robot, table = load_problem(args)
+        probs = [(args.src, args.robot, robot, table, 0, 1)]
+        config = workload_config(args, table) if args.config != 0 else \
+            {"workload": f"{args.robot} ({args.src} mapping), 1 synthetic clip x {T} frames (BASELINE.json configs[0]): latency view"}
+        metric = METRIC if args.robot == "unitree_g1" else f"retargeted frames/sec ({args.robot})"
+    np_ = len(probs)
     sub = lambda b, ids: type(b)(pos=b.pos[ids], quat=b.quat[ids], heights=b.heights[ids], qpos_gen=b.qpos_gen[ids])
-    run = lambda b: cpu_reference_run(robot, table, b, src=args.src, robot_name=args.robot)
-    # probe: the first 2 clips per core (at most 64) give the rate of whichever implementation is present
-    n_probe = min(C, max(2 * cores, 8), 64)
-    probe = make_clips(robot, table, range(n_probe), T=T, src_human=args.src)
-    _, _, dt, kind, note = run(probe)
-    rate = n_probe * T / dt
+
+    def run(batches):            # one pass: every robot's share, all host threads each
+        dt, kind, note = 0.0, "port", ""
+        for (src, name, robot, table, _, _), b in zip(probs, batches):
+            if b.pos.shape[0] == 0:
+                continue
+            _, _, d, kind, note = cpu_reference_run(robot, table, b, src=src, robot_name=name)
+            dt += d
+        return dt, kind, note
+
+    def gen(n_per):              # the first n_per clip ids of every robot's bucket
+        return [make_clips(robot, table, list(range(first, C, stride))[:n_per], T=T, src_human=src)
+                for (src, name, robot, table, first, stride) in probs]
+
+    # probe: a few clips per core (at most 64 in all) give the rate of whichever implementation is present
+    n_probe = max(1, min(C // np_, max(2 * cores, 8) // np_ + 1, 64 // np_ + 1))
+    probe = gen(n_probe)
+    dt, kind, note = run(probe)
+    rate = sum(b.pos.shape[0] for b in probe) * T / dt
     budget_s = float(os.environ.get("GMR_REF_BUDGET_S", "120"))
     passes = max(args.steps + max(args.warmup, 0), 1)
-    sample = int(min(C, max(cores, rate * budget_s / passes / T)))
-    n_gen = min(C, sample * passes)                       # only the clips some pass will touch are generated
-    clips = probe if n_gen <= n_probe else make_clips(robot, table, range(n_gen), T=T, src_human=args.src)
-    n_gen = clips.pos.shape[0]
-    ids_of = lambda k: [(k * sample + i) % n_gen for i in range(sample)]
+    per = int(max(1, min(C // np_, max(cores // np_, 1, rate * budget_s / passes / T / np_))))     # clips per robot per step
+    n_gen = min(max(C // np_, 1), per * passes)            # only the clips some pass will touch are generated
+    clips = probe if n_gen <= n_probe else gen(n_gen)
+    n_gen = min(b.pos.shape[0] for b in clips)
+    ids_of = lambda k: [(k * per + i) % n_gen for i in range(per)]
     k = 0
     for _ in range(max(args.warmup, 0)):
-        run(sub(clips, ids_of(k))); k += 1
+        run([sub(b, ids_of(k)) for b in clips]); k += 1
     times = []
     for _ in range(args.steps):
-        _, _, dt, _, _ = run(sub(clips, ids_of(k))); k += 1
+        dt, _, _ = run([sub(b, ids_of(k)) for b in clips]); k += 1
         times.append(dt)
     tot = sum(times)
+    sample = per * np_
     value = sample * T * args.steps / tot
     line = {
-        "metric": METRIC if args.robot == "unitree_g1" else f"retargeted frames/sec ({args.robot})", "value": value, "unit": "frames/s", "impl": "reference",
+        "metric": metric, "value": value, "unit": "frames/s", "impl": "reference",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, table),
+        "higher_is_better": True, "scaling": "strong" if args.config == 4 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config,
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
-                         "sample": f"each step = {sample} of the workload's {C} clips x {T} frames (rotating window over clip ids "
-                                   f"0..{n_gen - 1}), {args.steps} steps; {note}; {cores} host threads"},
+                         "sample": f"each step = {sample} of the workload's {C} clips x {T} frames (rotating window over the first "
+                                   f"{n_gen} clip ids of every robot), {args.steps} steps; {note}; {cores} host threads"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "published_reference_fps_single_process": "35-70 (README.md:215-221, desktop CPUs)",
     }
     print(json.dumps(line))
+
+
+MIXED_ROBOTS = ["unitree_g1", "booster_t1", "stanford_toddy", "fourier_n1", "engineai_pm01"]   # BASELINE.json configs[4], smplx mapping
+
+
+def read_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def setup_dist():
+    """(world, rank, local, dev, barrier, maxreduce, sumreduce); NCCL only carries the barrier and the reductions of the timing."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        # NCCL prints its "NCCL version ..." banner on stdout when the communicator is created; stdout must carry
+        # the one JSON line only, so fd 1 points at stderr while the communicator comes up
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def reduce(x: float, op) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    return (world, rank, local, dev, barrier, lambda x: reduce(x, dist.ReduceOp.MAX), lambda x: reduce(x, dist.ReduceOp.SUM))
+
+
+def main_trace(args):
+    """BASELINE.json configs[0]: ONE clip x 300 frames.  The reference's own CPU-runnable case; here it is the latency view of
+    the kernel: the clip as one batch (a lone warp on one SM) and frame by frame through the live-stream entry
+    (GeneralMotionRetargeting.retarget, one C call per frame), with the per-frame iteration histogram."""
+    import torch
+    from general_motion_retargeting_b200 import GeneralMotionRetargeting
+    from general_motion_retargeting_b200.synthetic import make_clips
+    robot, table = load_problem(args)
+    T = args.frames
+    torch.cuda.set_device(0)
+    clips = make_clips(robot, table, range(1), T=T, src_human=args.src)
+    gmr = GeneralMotionRetargeting(args.src, args.robot, device=0)
+    dp, dq, dh = (torch.from_numpy(x).cuda() for x in (clips.pos, clips.quat, clips.heights))
+    q, it, err = gmr.retarget_batch(dp, dq, dh, return_info=True, precision=args.precision)
+    for _ in range(max(args.warmup, 3)):
+        gmr.retarget_batch(dp, dq, dh, precision=args.precision)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        gmr.retarget_batch(dp, dq, dh, precision=args.precision)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    itn = it.cpu().numpy()[0]
+    # live stream: one retarget() per frame, warm-started, like scripts/smplx_to_robot.py:104-140
+    names = gmr.human_body_names
+    frames = [{n: (clips.pos[0, t, i].astype(np.float64), clips.quat[0, t, i].astype(np.float64)) for i, n in enumerate(names)} for t in range(T)]
+    live = GeneralMotionRetargeting(args.src, args.robot, actual_human_height=float(clips.heights[0]), device=0)
+    lat = []
+    qs = np.zeros((T, robot.nq))
+    for rep in range(2):                                   # the first pass warms the stream (graph capture)
+        live = GeneralMotionRetargeting(args.src, args.robot, actual_human_height=float(clips.heights[0]), device=0)
+        lat = []
+        for t in range(T):
+            t0 = time.perf_counter(); qs[t] = live.retarget(frames[t]); lat.append(time.perf_counter() - t0)
+    lat_us = np.array(lat) * 1e6
+    from oracle import native
+    t0 = time.perf_counter()
+    q_ref, it_ref, _ = native.retarget_batch(robot, table, clips.pos, clips.quat, clips.ratio(table), nthreads=1)
+    cpu_s = time.perf_counter() - t0
+    hist = lambda a: {int(k): int(v) for k, v in zip(*np.unique(a, return_counts=True))}
+    line = {"metric": METRIC, "value": T / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"{args.robot} ({args.src} mapping), 1 synthetic clip x {T} frames (BASELINE.json configs[0]): latency view"},
+            "gpu_launches": 1,
+            "trace": {"batch_us_per_frame": ms * 1e3 / T, "solves_per_frame": float(itn.sum() / T),
+                      "iterations_stage1_hist": hist(itn[:, 0]), "iterations_stage2_hist": hist(itn[:, 1]),
+                      "live_stream_us_per_frame": {"p50": float(np.percentile(lat_us, 50)), "p90": float(np.percentile(lat_us, 90)),
+                                                   "p99": float(np.percentile(lat_us, 99)), "max": float(lat_us.max()), "frame0": float(lat_us[0])},
+                      "live_stream_frames_per_s": float(T / np.sum(lat)),
+                      "live_vs_batch_max_abs_dqpos": float(np.abs(qs - q[0].double().cpu().numpy()).max())},
+            "e2e": {"value": float(T / np.sum(lat)), "unit": "frames/s", "h2d_bytes_per_step": int(T * table.nh * 28),
+                    "d2h_bytes_per_step": int(T * robot.nq * 8), "api": "GeneralMotionRetargeting.retarget(frame) per frame (live stream)"},
+            "cpu_baseline": {"value": T / cpu_s, "unit": "frames/s", "cores": 1, "kind": "port",
+                             "sample": f"the same clip, float64 C++ oracle port, 1 thread, {cpu_s:.2f} s"},
+            "parity": {"iteration_count_agreement": float((itn == it_ref[0]).all(-1).mean()),
+                       "max_abs_dqpos": float(np.abs(q[0].double().cpu().numpy() - q_ref[0]).max())}}
+    print(json.dumps(line))
+
+
+def mixed_problem(args, world):
+    """configs[4]: args.clips clips in all (strong scaling), clip i -> robot i mod 5, smplx mapping; per robot the clips are
+    dealt to the ranks by the hardness proxy.  Returns [(robot name, robot, table, [ids per rank])]."""
+    from general_motion_retargeting_b200 import params
+    from general_motion_retargeting_b200.ik_config import compile_task_table
+    from general_motion_retargeting_b200.sharding import hardness_proxy, lpt_shard, all_shards
+    from general_motion_retargeting_b200.synthetic import make_clips
+    out = []
+    for k, name in enumerate(MIXED_ROBOTS):
+        robot, cfg, _ = params.load_pack("smplx", name)
+        table = compile_task_table(robot, cfg)
+        ids = np.arange(k, args.clips, len(MIXED_ROBOTS))
+        if world > 1 and args.shard == "lpt":
+            import torch
+            f0 = make_clips(robot, table, ids.tolist(), T=1, src_human="smplx", device="cuda" if torch.cuda.is_available() else "cpu")
+            hard = hardness_proxy(f0.quat[:, 0], table.root_idx, table.rot_off[table.root_idx], robot.qpos0[3:7])
+            per_rank = [ids[x] for x in lpt_shard(hard, world)]
+        else:
+            per_rank = [ids[b:e] for b, e in all_shards(len(ids), world)]
+        out.append((name, robot, table, per_rank))
+    return out
+
+
+def mixed_config(args):
+    return {"workload": f"{args.clips} synthetic clips x {args.frames} frames in all, clip i -> robot i mod 5 of "
+                        f"{'/'.join(MIXED_ROBOTS)} (smplx mapping), sharded by clip over the GPUs (BASELINE.json configs[4])",
+            "clips_total": args.clips, "frames": args.frames,
+            "sharding": ("per robot, clips dealt to the ranks by a hardness proxy (sharding.lpt_shard), " if args.shard == "lpt" else
+                         "per robot, contiguous ranges per rank, ") + "no collective on the solve path",
+            "l2": "inputs of every bucket exceed the 126 MB L2"}
+
+
+def main_mixed(args):
+    import torch
+    from general_motion_retargeting_b200 import GeneralMotionRetargeting, _native, retarget_mixed
+    from general_motion_retargeting_b200.synthetic import make_clips
+    world, rank, local, dev, barrier, maxreduce, sumreduce = setup_dist()
+    T = args.frames
+    prob = mixed_problem(args, world)
+    lib = _native.load_library()
+    buckets_dev, buckets_host, host_clips, gm = [], [], [], []
+    for name, robot, table, per_rank in prob:
+        ids = per_rank[rank].tolist()
+        clips = make_clips(robot, table, ids, T=T, src_human="smplx", device=str(dev))
+        g = GeneralMotionRetargeting("smplx", name, device=local)
+        gm.append(g); host_clips.append(clips)
+        buckets_dev.append((g, torch.from_numpy(clips.pos).to(dev), torch.from_numpy(clips.quat).to(dev), torch.from_numpy(clips.heights).to(dev)))
+    my_frames = sum(len(p[3][rank]) for p in prob) * T
+    all_frames = args.clips * T
+
+    outs, its = retarget_mixed(buckets_dev, precision=args.precision, return_info=True)
+    torch.cuda.synchronize(dev)
+    iters = [x.cpu().numpy() for x in its]
+    flops_step = sum(flops_of_run(robot, table, it) for (_, robot, table, _), it in zip(prob, iters))
+    q_dev = [o.double().cpu().numpy() for o in outs]
+    del outs, its
+    for _ in range(args.warmup):
+        retarget_mixed(buckets_dev, precision=args.precision)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.gmr_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for k in range(args.steps):
+        retarget_mixed(buckets_dev, precision=args.precision)
+        ev[k + 1].record()
+    barrier()
+    launches = lib.gmr_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = maxreduce(ev[0].elapsed_time(ev[-1]))
+    kernel_ms_avg = total_ms / args.steps
+    value = all_frames * args.steps / (total_ms * 1e-3)
+    flops_all = sumreduce(flops_step)
+
+    e2e, e2e_check = None, None
+    if not args.no_e2e:
+        del buckets_dev
+        torch.cuda.empty_cache()
+        for g, clips in zip(gm, host_clips):
+            buckets_host.append((g, torch.from_numpy(clips.pos).pin_memory(), torch.from_numpy(clips.quat).pin_memory(), torch.from_numpy(clips.heights)))
+        for _ in range(max(1, min(args.warmup, 2))):
+            outs = retarget_mixed(buckets_host, precision=args.precision, device=local)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            outs = retarget_mixed(buckets_host, precision=args.precision, device=local)
+        torch.cuda.synchronize(dev)
+        e2e_s = maxreduce(time.perf_counter() - t0)
+        h2d = sum(b[1].numel() * 4 + b[2].numel() * 4 + b[3].numel() * 4 for b in buckets_host)
+        d2h = sum(o.numel() * 4 for o in outs)
+        e2e = {"value": all_frames * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(sumreduce(h2d)),
+               "d2h_bytes_per_step": int(sumreduce(d2h)), "ms_per_step": 1e3 * e2e_s / args.steps,
+               "api": "retarget_mixed(buckets of pinned host tensors) -> gmr_retarget_multi: the kernels read the keypoints over the host "
+                      "link and write qpos into pinned output tensors (allocated inside the timed call); wall clock, max over ranks"}
+        e2e_check = max(float(np.abs(o.numpy().astype(np.float64) - qd).max()) for o, qd in zip(outs, q_dev))
+
+    cpu_baseline, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        per = max(8 * cores, 16)                      # clips per robot: ~10 s of CPU work in all
+        dt_all, parity = 0.0, {}
+        for (name, robot, table, _), clips, it, qd in zip(prob, host_clips, iters, q_dev):
+            n = min(per, clips.pos.shape[0])
+            sub = type(clips)(pos=clips.pos[:n], quat=clips.quat[:n], heights=clips.heights[:n], qpos_gen=clips.qpos_gen[:n])
+            q_ref, it_ref, dt, kind, note = cpu_reference_run(robot, table, sub)
+            dt_all += dt
+            same = (it[:n] == it_ref).all(-1)
+            dq = np.abs(qd[:n] - q_ref).max(-1)
+            prefix = np.logical_and.accumulate(same, axis=1)
+            parity[name] = {"frames": int(same.size), "iteration_count_agreement": float(same.mean()), "max_abs_dqpos_all": float(dq.max()),
+                            "max_abs_dqpos_identical_history": float(dq[prefix].max()) if prefix.any() else None}
+        nclips = sum(min(per, c.pos.shape[0]) for c in host_clips)
+        cpu_baseline = {"value": nclips * T / dt_all, "unit": "frames/s", "cores": cores, "kind": kind,
+                        "sample": f"first {per} clips of every robot x {T} frames ({nclips} clips), {note}, {cores} host threads, {dt_all:.1f} s"}
+    if rank == 0:
+        peaks = read_peaks()
+        sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        nsm = torch.cuda.get_device_properties(dev).multi_processor_count
+        lanes = 128 if args.precision == "f32" else 64
+        peak_tf = world * nsm * lanes * 2 * sm_max * 1e6 / 1e12
+        achieved_tf = flops_all / (kernel_ms_avg * 1e-3) / 1e12
+        line = {"metric": "retargeted frames/sec (mixed robots: g1/t1/toddy/n1/pm01)", "value": value, "unit": "frames/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms_avg, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": mixed_config(args),
+                "solves_per_frame": float(sum(it.sum() for it in iters) / max(my_frames, 1)), "gpu_launches": int(launches), "clocks": clocks,
+                "e2e": e2e,
+                "roofline": {"bound": "fp32_fma" if args.precision == "f32" else "fp64_fma", "achieved": achieved_tf, "peak": peak_tf,
+                             "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+                             "peak_basis": f"{world} GPUs x {nsm} SMs x {lanes} lanes x 2 x {sm_max:.0f} MHz", "flops_per_step": flops_all,
+                             "kernel_ms": kernel_ms_avg},
+                "cpu_baseline": cpu_baseline, "parity": parity, "e2e_vs_device_max_abs_diff": e2e_check}
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
 
 
 def main_ours(args):
@@ -235,8 +531,17 @@ def main_ours(args):
 
     robot, table = load_problem(args)
     C, T = args.clips, args.frames
-    # rank r owns clips [r*C, (r+1)*C): contiguous clip ranges, no data-path collective
-    clips = make_clips(robot, table, range(rank * C, (rank + 1) * C), T=T, src_human=args.src, device=str(dev))
+    # weak scaling: world x C clips in all, C per rank, no data-path collective.  Which C: a contiguous range, or (default)
+    # the hardness-aware deal - every rank computes the same assignment from frame 0 of all clips (cheap: one frame each)
+    if world > 1 and args.shard == "lpt":
+        from general_motion_retargeting_b200.sharding import hardness_proxy, lpt_shard
+        f0 = make_clips(robot, table, range(world * C), T=1, src_human=args.src, device=str(dev))
+        hard = hardness_proxy(f0.quat[:, 0], table.root_idx, table.rot_off[table.root_idx], robot.qpos0[3:7])
+        my_ids = lpt_shard(hard, world)[rank].tolist()
+        del f0
+    else:
+        my_ids = range(rank * C, (rank + 1) * C)
+    clips = make_clips(robot, table, my_ids, T=T, src_human=args.src, device=str(dev))
     gmr = GeneralMotionRetargeting(args.src, args.robot, device=local)
     lib = _native.load_library()
 
@@ -290,7 +595,8 @@ def main_ours(args):
     frames_step_all = world * C * T
     value = frames_step_all * args.steps / (total_ms * 1e-3)
 
-    # ---- float32 fast mode, same workload (reported beside the headline, never instead of it) -----
+    # ---- float32 APPROXIMATE mode, same workload: reported beside the headline, never instead of it; it is outside the
+    # parity gate (max |dqpos| <= 1e-3 rad) on ill-conditioned clips, which the line states with the measured numbers -----
     f32_side = None
     if args.precision == "f64" and not args.no_f32:
         q32, it32, _ = gmr.retarget_batch(d_pos, d_quat, d_h, return_info=True, precision="f32")
@@ -310,6 +616,8 @@ def main_ours(args):
         dq = np.abs(dq).max(-1)
         prefix = np.logical_and.accumulate(same[: dq.shape[0]], axis=1)
         f32_side = {"value": frames_step_all * args.steps / (ms32 * 1e-3), "unit": "frames/s", "ms_per_step": ms32 / args.steps,
+                    "label": "approximate mode, NOT a parity-grade result",
+                    "within_parity_gate_1e-3": bool(float(dq[prefix].max()) < 1e-3 and float(dq.max()) < 1e-3),
                     "vs_f64_kernel": {"iteration_count_agreement": float(same.mean()),
                                       "max_abs_dqpos_identical_history": float(dq[prefix].max()),
                                       "max_abs_dqpos_all": float(dq.max()), "p999_abs_dqpos": float(np.quantile(dq, 0.999))}}
@@ -428,7 +736,7 @@ def main_ours(args):
             "cpu_baseline": cpu_baseline,
             "parity": parity,
             "e2e_vs_device_max_abs_diff": e2e_check,
-            "f32_fast_mode": f32_side,
+            "f32_approximate_mode": f32_side,
         }
         print(json.dumps(line))
     if world > 1:
@@ -439,5 +747,9 @@ if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         main_reference(a)
+    elif a.config == 0:
+        main_trace(a)
+    elif a.config == 4:
+        main_mixed(a)
     else:
         main_ours(a)

@@ -39,13 +39,17 @@ struct GmrConsts {
   uint32_t lvl_mask[GMR_MAXD + 2];    // [d] -> bitmask of the hinges of depth d (1-based)
   uint8_t hdepth[GMR_NH];             // hinge i -> number of hinges on the chain root .. i (inclusive); 0 for unused lanes
   uint8_t anc_of[GMR_NH * GMR_MAXD];  // [i][d-1] -> the hinge at depth d on i's chain (d <= hdepth[i]; own index at d = hdepth[i])
-  // forward-kinematics records, one per body in level order (entry e of lvl_body): what one lane needs to
-  // place its body, in three 128-bit loads.  The body's rotation in the parent frame is
-  // bquat * quat(axis, q) = cos(q/2) * A + sin(q/2) * B  with A = bquat, B = bquat * (0, axis).
-  uint32_t fk_idx[GMR_MAX_BODY];      // body | parent << 8 | (hinge, or nh for a fixed body) << 16
-  alignas(16) R fk_pos[GMR_MAX_BODY * 4];   // offset in the parent frame, pad (16-byte aligned: read with 128-bit loads)
+  // Forward-kinematics records.  FK is a pointer-jumping scan over the tree of MOVING bodies (hinge bodies + the root):
+  // fixed bodies between two hinges are folded into constants on the host.
+  //   entries [0, nh): hinge j.  Its body's pose in the frame of its nearest moving ancestor is
+  //     ( P, cos(q/2) * A + sin(q/2) * B ),  A = (fixed transforms) * bquat,  B = A * (0, axis);
+  //     fk_idx[j] = four bytes: the BODY index of the moving ancestor at distance 1, 2, 4, 8 (0xff: none)
+  //   entries [nh, nh + nfix): a fixed body: fk_idx = body | body of its nearest moving ancestor << 8, (fk_pos, fk_A) = its
+  //     constant pose in that ancestor's frame
+  uint32_t fk_idx[GMR_MAX_BODY];
+  alignas(16) R fk_pos[GMR_MAX_BODY * 4];   // 16-byte aligned: read with 128-bit loads
   alignas(16) R fk_A[GMR_MAX_BODY * 4];
-  alignas(16) R fk_B[GMR_MAX_BODY * 4];     // zero for a fixed body
+  alignas(16) R fk_B[GMR_MAX_BODY * 4];
   R axis[GMR_NH * 3];
   R lo[GMR_NH], hi[GMR_NH];
   R qpos0[8 + GMR_NH];
@@ -92,6 +96,7 @@ inline int gmr_fill_consts(const GmrModelDesc* d, GmrConsts<R>* c, const char** 
   if (d->nbody < 1 || d->nhinge < 0 || d->nhuman < 1 || d->ntask < 1) return fail(GMR_EINVAL, "empty model");
   if (d->nbody > GMR_MAX_BODY) return fail(GMR_ELIMIT, "too many bodies (GMR_MAX_BODY)");
   if (d->nhinge > GMR_MAX_HINGE) return fail(GMR_ELIMIT, "too many hinges (GMR_MAX_HINGE)");
+  if (d->nhinge > GMR_NH - 1) return fail(GMR_ELIMIT, "more than 31 hinges: the FK scan keeps one lane for the floating root");
   if (d->nhuman > GMR_MAX_HUMAN) return fail(GMR_ELIMIT, "too many human bodies (GMR_MAX_HUMAN)");
   if (d->ntask > GMR_MAX_TASK) return fail(GMR_ELIMIT, "too many tasks (GMR_MAX_TASK)");
   if (!d->body_parent || !d->body_pos || !d->body_quat || !d->body_hinge || !d->qpos0 || !d->human_scale ||
@@ -158,18 +163,53 @@ inline int gmr_fill_consts(const GmrModelDesc* d, GmrConsts<R>* c, const char** 
     for (int i = 0; i < m.nh; i++) if ((m.anc_mask[j] >> i) & 1u) m.desc_mask[i] |= 1u << j;
   }
   for (int j = 0; j < m.nh; j++) m.lvl_mask[m.hdepth[j]] |= 1u << j;
-  for (int e = 0; e < m.nb; e++) {
-    const int b = m.lvl_body[e], j = m.bhinge[b];
-    m.fk_idx[e] = (uint32_t)b | ((uint32_t)(m.parent[b] < 0 ? 0 : m.parent[b]) << 8) | ((uint32_t)(j >= 0 ? j : m.nh) << 16);
-    const double* bq = d->body_quat + 4 * b;
-    for (int k = 0; k < 3; k++) m.fk_pos[4 * e + k] = R(d->body_pos[3 * b + k]);
-    for (int k = 0; k < 4; k++) m.fk_A[4 * e + k] = R(bq[k]);
-    if (j >= 0) {
-      const double* ax = d->hinge_axis + 3 * j;                 // bquat * (0, axis)
-      m.fk_B[4 * e + 0] = R(-bq[1] * ax[0] - bq[2] * ax[1] - bq[3] * ax[2]);
-      m.fk_B[4 * e + 1] = R(bq[0] * ax[0] + bq[2] * ax[2] - bq[3] * ax[1]);
-      m.fk_B[4 * e + 2] = R(bq[0] * ax[1] - bq[1] * ax[2] + bq[3] * ax[0]);
-      m.fk_B[4 * e + 3] = R(bq[0] * ax[2] + bq[1] * ax[1] - bq[2] * ax[0]);
+  { // FK scan tables (see fk_idx above): fold the fixed bodies above every body into a constant transform
+    auto qmul = [](const double* a, const double* b, double* o) {
+      const double w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                   y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+      o[0] = w; o[1] = x; o[2] = y; o[3] = z;
+    };
+    auto qrot = [](const double* q, const double* v, double* o) {
+      const double tx = 2 * (q[2] * v[2] - q[3] * v[1]), ty = 2 * (q[3] * v[0] - q[1] * v[2]), tz = 2 * (q[1] * v[1] - q[2] * v[0]);
+      const double ox = v[0] + q[0] * tx + (q[2] * tz - q[3] * ty), oy = v[1] + q[0] * ty + (q[3] * tx - q[1] * tz),
+                   oz = v[2] + q[0] * tz + (q[1] * ty - q[2] * tx);
+      o[0] = ox; o[1] = oy; o[2] = oz;
+    };
+    int anchor[GMR_MAX_BODY];            // nearest moving strict ancestor (a hinge body or the root), -1 for the root
+    int nfix = 0;
+    anchor[0] = -1;
+    for (int b = 1; b < m.nb; b++) {
+      double pa[3] = {d->body_pos[3 * b], d->body_pos[3 * b + 1], d->body_pos[3 * b + 2]};
+      double qa[4] = {d->body_quat[4 * b], d->body_quat[4 * b + 1], d->body_quat[4 * b + 2], d->body_quat[4 * b + 3]};
+      int cur = m.parent[b];
+      while (cur > 0 && m.bhinge[cur] < 0) {            // a fixed body in between: compose its constant pose in front
+        double t[3]; qrot(d->body_quat + 4 * cur, pa, t);
+        for (int k = 0; k < 3; k++) pa[k] = d->body_pos[3 * cur + k] + t[k];
+        double q2[4]; qmul(d->body_quat + 4 * cur, qa, q2);
+        for (int k = 0; k < 4; k++) qa[k] = q2[k];
+        cur = m.parent[cur];
+      }
+      anchor[b] = cur;
+      const int j = m.bhinge[b];
+      const int e = j >= 0 ? j : m.nh + nfix++;
+      for (int k = 0; k < 3; k++) m.fk_pos[4 * e + k] = R(pa[k]);
+      for (int k = 0; k < 4; k++) m.fk_A[4 * e + k] = R(qa[k]);
+      if (j >= 0) {
+        const double ax[4] = {0.0, d->hinge_axis[3 * j], d->hinge_axis[3 * j + 1], d->hinge_axis[3 * j + 2]};
+        double B[4]; qmul(qa, ax, B);
+        for (int k = 0; k < 4; k++) m.fk_B[4 * e + k] = R(B[k]);
+      } else {
+        m.fk_idx[e] = (uint32_t)b | ((uint32_t)cur << 8);
+      }
+    }
+    for (int j = 0; j < m.nh; j++) {                    // moving ancestors at distance 1, 2, 4, 8
+      uint32_t packed = 0;
+      for (int k = 0; k < 4; k++) {
+        int a = m.hbody[j];
+        for (int s = 0; s < (1 << k) && a >= 0; s++) a = anchor[a];
+        packed |= (uint32_t)(a >= 0 ? a : 0xff) << (8 * k);
+      }
+      m.fk_idx[j] = packed;
     }
   }
   for (int i = 0; i < m.nq; i++) m.qpos0[i] = R(d->qpos0[i]);

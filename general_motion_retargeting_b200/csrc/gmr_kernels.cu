@@ -380,6 +380,7 @@ struct GmrModel {
   // lazily created resources of the host-buffer entry
   std::mutex host_mu;
   cudaStream_t hs[2] = {nullptr, nullptr};
+  cudaStream_t ms[8] = {};       // side streams of gmr_retarget_multi (created on first use, guarded by host_mu)
 };
 
 namespace {
@@ -422,11 +423,12 @@ inline int ctas_per_sm() {
   static const int n = [] { const char* e = getenv("GMR_CTAS_PER_SM"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : (v > 7 ? 7 : v); }();
   return n;
 }
-template <typename R> int pick_wpc(const GmrModel* m, int C) {
+template <typename R> int pick_wpc(const GmrModel* m, int C, int sms = 0) {
+  if (sms <= 0) sms = m->num_sms;
   int wpc = max_warps<R>() / ctas_per_sm();
   if (const char* cap = getenv("GMR_WPC_CAP")) { int c = atoi(cap); if (c >= 1 && c < wpc) wpc = c; }   // tuning knob
   while (wpc > 1 && smem_bytes<R>(m, wpc) > (size_t)m->max_smem) wpc--;
-  int need = (C + m->num_sms * ctas_per_sm() - 1) / (m->num_sms * ctas_per_sm());
+  int need = (C + sms * ctas_per_sm() - 1) / (sms * ctas_per_sm());
   if (need < 1) need = 1;
   if (need < wpc) wpc = need;
   return wpc;
@@ -435,12 +437,14 @@ template <typename R> int pick_wpc(const GmrModel* m, int C) {
 template <typename R, typename IO, int MAXWARPS>
 int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* quat, const float* ratio, int C, int T,
            const IO* qinit, IO* qout, int32_t* iters, IO* err, IO* tg, uint32_t flags, cudaStream_t st,
-           const GmrBatchExtra* extra = nullptr, int* own_queue = nullptr) {
+           const GmrBatchExtra* extra = nullptr, int* own_queue = nullptr, int sm_share = 0) {
+  // sm_share > 0: this launch may use only that many SMs (CTAs); other launches run beside it (gmr_retarget_multi)
   if (C == 0 || T == 0) return GMR_OK;
+  const int sms = sm_share > 0 && sm_share < m->num_sms ? sm_share : m->num_sms;
   GmrBatchExtra ex{};
   if (extra) ex = *extra;
   auto kern = gmr_retarget_kernel<R, IO, MAXWARPS>;
-  const int wpc = pick_wpc<R>(m, C);
+  const int wpc = pick_wpc<R>(m, C, sms);
   const size_t smem = smem_bytes<R>(m, wpc);
   if (smem > (size_t)m->max_smem) return set_err(GMR_ELIMIT, "model does not fit in shared memory");
   // opt in to the large dynamic allocation: once per (kernel instantiation, device) — the attribute is per device
@@ -451,7 +455,7 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
     configured.fetch_or(dev_bit, std::memory_order_release);
   }
   int grid = (C + wpc - 1) / wpc;
-  if (grid > m->num_sms * ctas_per_sm()) grid = m->num_sms * ctas_per_sm();
+  if (grid > sms * ctas_per_sm()) grid = sms * ctas_per_sm();
   // convoy mode (see gmr_solver.cuh) paid off while the hot path was 3x the instruction cache; with the
   // branch-sparse factorisation free-running warps are as fast on balanced batches and 8-10 % faster on
   // mixed ones (a slow clip no longer drags its CTA through a rendezvous per factorisation).  GMR_CONVOY=1 re-enables.
@@ -478,7 +482,7 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
   static const int seg_env = getenv("GMR_SEGMENT") ? atoi(getenv("GMR_SEGMENT")) : 25;
   static const double slow_err_env = getenv("GMR_SLOW_ERR") ? atof(getenv("GMR_SLOW_ERR")) : 1.0;
   const bool two_phase = part_env > 0 && seg_env > 0 && !own_queue && !convoy && !(flags & GMR_FLAG_NO_SOLVE) && T >= 16 &&
-                         C > 2 * m->num_sms * part_env;
+                         C > 2 * sms * part_env;
   if (two_phase) {
     const int stride = gmr_state_stride(dims.nq), cap = 2 * C + 2;
     const size_t b_state = ((size_t)C * stride * sizeof(double) + 255) & ~(size_t)255, b_ring = (size_t)2 * cap * sizeof(long long);
@@ -584,6 +588,7 @@ int gmr_model_create(const GmrModelDesc* desc, int device, GmrModel** out) {
 int gmr_model_destroy(GmrModel* m) {
   if (!m) return GMR_OK;
   DeviceGuard g(m->device);
+  for (auto& st : m->ms) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
   for (int i = 0; i < 2; i++) {
     if (m->hs[i]) { cudaStreamSynchronize(m->hs[i]); cudaStreamDestroy(m->hs[i]); }
   }
@@ -741,10 +746,50 @@ int gmr_retarget_multi(const GmrBatchDesc* batches, int32_t n, uint32_t flags, v
     if (!d.pos || !d.quat || !d.qpos_out) return set_err(GMR_EINVAL, "pos, quat and qpos_out are required");
     if ((reinterpret_cast<uintptr_t>(d.quat) & 15u) != 0) return set_err(GMR_EINVAL, "quat must be 16-byte aligned");
   }
-  DeviceGuard g(batches[0].model->device);
+  GmrModel* m0 = batches[0].model;
+  DeviceGuard g(m0->device);
   if (!g.ok) return set_err(GMR_ECUDA, "cannot select the models' device");
-  if (flags & GMR_FLAG_COMPUTE_F64) return launch_multi<double, MAXW_F64>(batches, n, flags, (cudaStream_t)cuda_stream);
-  return launch_multi<float, MAXW_F32>(batches, n, flags, (cudaStream_t)cuda_stream);
+  static const int one_kernel = getenv("GMR_MULTI_KERNEL") ? atoi(getenv("GMR_MULTI_KERNEL")) : 0;
+  if (one_kernel || m0->num_sms < 2 * n) {
+    if (flags & GMR_FLAG_COMPUTE_F64) return launch_multi<double, MAXW_F64>(batches, n, flags, (cudaStream_t)cuda_stream);
+    return launch_multi<float, MAXW_F32>(batches, n, flags, (cudaStream_t)cuda_stream);
+  }
+  // Default: every bucket is an ordinary single-robot batch (two-phase / scheduled launch included) confined to its share
+  // of the SMs, all buckets side by side on the first model's side streams, joined back into the caller's stream.  The
+  // shares follow the work: clips x frames x DoFs (the per-frame cost grows with the size of the system).
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  double work[GMR_MAX_MULTI], total = 0;
+  for (int i = 0; i < n; i++) { work[i] = (double)batches[i].C * batches[i].T * (6 + batches[i].model->h_f32.nh); total += work[i]; }
+  int share[GMR_MAX_MULTI], used = 0;
+  for (int i = 0; i < n; i++) { share[i] = (int)(m0->num_sms * work[i] / total); if (share[i] < 1) share[i] = 1; used += share[i]; }
+  for (int i = 0; used < m0->num_sms; i = (i + 1) % n) { share[i]++; used++; }       // hand out the remainder
+  for (int i = 0; used > m0->num_sms; i = (i + 1) % n) if (share[i] > 1) { share[i]--; used--; }
+  std::lock_guard<std::mutex> lk(m0->host_mu);
+  cudaEvent_t fork = nullptr, join[GMR_MAX_MULTI] = {};
+  int rc = GMR_OK;
+  auto cleanup = [&]() { if (fork) cudaEventDestroy(fork); for (auto& e : join) if (e) cudaEventDestroy(e); };
+  #define CKM(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { cleanup(); return cuda_err(_e, #call); } } while (0)
+  CKM(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+  CKM(cudaEventRecord(fork, st));
+  for (int i = 0; i < n && rc == GMR_OK; i++) {
+    if (!m0->ms[i]) CKM(cudaStreamCreateWithFlags(&m0->ms[i], cudaStreamNonBlocking));
+    cudaStream_t si = m0->ms[i];
+    CKM(cudaStreamWaitEvent(si, fork, 0));
+    const GmrBatchDesc& d = batches[i];
+    if (flags & GMR_FLAG_COMPUTE_F64)
+      rc = launch<double, float, MAXW_F64>(d.model, d.model->d_f64, d.pos, d.quat, d.ratio, d.C, d.T, d.qpos_init, d.qpos_out,
+                                           d.iters_out, d.err_out, nullptr, flags, si, nullptr, nullptr, share[i]);
+    else
+      rc = launch<float, float, MAXW_F32>(d.model, d.model->d_f32, d.pos, d.quat, d.ratio, d.C, d.T, d.qpos_init, d.qpos_out,
+                                          d.iters_out, d.err_out, nullptr, flags, si, nullptr, nullptr, share[i]);
+    if (rc != GMR_OK) break;
+    CKM(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming));
+    CKM(cudaEventRecord(join[i], si));
+    CKM(cudaStreamWaitEvent(st, join[i], 0));
+  }
+  #undef CKM
+  cleanup();                                                       // destruction is deferred until the events have completed
+  return rc;
 }
 
 // ---- single live stream ---------------------------------------------------------------------------------

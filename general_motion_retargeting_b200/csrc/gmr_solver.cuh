@@ -448,53 +448,97 @@ struct WarpSolver {
 
   // forward kinematics of s_q -> s_xp (root-relative positions), s_xq (world orientations),
   // then the world-frame spatial axis of every hinge at the root origin -> s_sd[j] = (v, w).
+  //
+  // A pointer-jumping scan over the tree of MOVING bodies instead of a walk by tree level: lane j < nh owns hinge j's body,
+  // lane nh the floating root; fixed bodies in between are folded into the records on the host (gmr_fill_consts).  Every lane
+  // starts from its pose in its moving parent's frame, (P, cos(q/2) A + sin(q/2) B), and in step k composes the pose its
+  // ancestor at distance 2^k has accumulated so far in front of its own: after ceil(log2(depth + 1)) steps (4 for G1's 10
+  // hinges + root) every lane holds its world pose - 4 dependent compositions on 30 lanes instead of 11 on 2-6.  The
+  // running pose stays in registers; each step reads the ancestor's from shared memory (one block) and publishes its
+  // own (next block).  Fixed bodies (hands, head, sensors: task frames and the epilogue need them) follow in one block.
   GMR_FN void fk() {
+    R q[4] = {R(1), R(0), R(0), R(0)}, p[3] = {R(0), R(0), R(0)};
+#ifdef GMR_EMULATE
+    R eq[32][4], ep[32][3];
+#define GMR_FK_LOAD for (int i_ = 0; i_ < 4; i_++) q[i_] = eq[lane][i_]; for (int i_ = 0; i_ < 3; i_++) p[i_] = ep[lane][i_];
+#define GMR_FK_SAVE for (int i_ = 0; i_ < 4; i_++) eq[lane][i_] = q[i_]; for (int i_ = 0; i_ < 3; i_++) ep[lane][i_] = p[i_];
+#else
+#define GMR_FK_LOAD
+#define GMR_FK_SAVE
+#endif
     GMR_LANES
       if (lane < dm.nh) {
         R s, c; g_sincos(R(0.5) * s_q()[7 + lane], &s, &c);
-        s_sc()[2 * lane] = s; s_sc()[2 * lane + 1] = c;
-      }
-      if (lane == 0) {
-        s_sc()[2 * dm.nh] = R(0); s_sc()[2 * dm.nh + 1] = R(1);          // the "hinge" of fixed bodies
-        R q[4] = {s_q()[3], s_q()[4], s_q()[5], s_q()[6]};
+        R A[4], B[4], P[4];
+        g_ld4(mc.fk_A + 4 * lane, A); g_ld4(mc.fk_B + 4 * lane, B); g_ld4(mc.fk_pos + 4 * lane, P);
+        q[0] = c * A[0] + s * B[0]; q[1] = c * A[1] + s * B[1]; q[2] = c * A[2] + s * B[2]; q[3] = c * A[3] + s * B[3];
+        p[0] = P[0]; p[1] = P[1]; p[2] = P[2];
+        const int b = mc.hbody[lane];
+        g_st4(s_xq() + 4 * b, q[0], q[1], q[2], q[3]);
+        g_st4(s_xp() + 4 * b, p[0], p[1], p[2], R(0));
+      } else if (lane == dm.nh) {
+        q[0] = s_q()[3]; q[1] = s_q()[4]; q[2] = s_q()[5]; q[3] = s_q()[6];
         q_normalize(q);
+        p[0] = p[1] = p[2] = R(0);
         g_st4(s_xq(), q[0], q[1], q[2], q[3]);
         g_st4(s_xp(), R(0), R(0), R(0), R(0));
         g_st4(s_rq(), q[0], q[1], q[2], q[3]);
       }
+      GMR_FK_SAVE
     GMR_END
-    for (int l = 1; l < dm.nlevel; l++) {
-      const int beg = mc.lvl_off[l], cnt = mc.lvl_off[l + 1] - beg;
-      GMR_LANES
-        for (int e = beg + lane; e < beg + cnt; e += 32) {
-          const uint32_t ix = mc.fk_idx[e];
-          const int b = ix & 0xffu, p = (ix >> 8) & 0xffu, j = ix >> 16;
-          R pq[4], pp[4], bp[4], A[4], B[4];
-          g_ld4(s_xq() + 4 * p, pq); g_ld4(s_xp() + 4 * p, pp);
-          g_ld4(mc.fk_pos + 4 * e, bp); g_ld4(mc.fk_A + 4 * e, A); g_ld4(mc.fk_B + 4 * e, B);
-          const R sn = s_sc()[2 * j], cs = s_sc()[2 * j + 1];
-          R off[3]; q_rot(pq, bp, off);
-          g_st4(s_xp() + 4 * b, pp[0] + off[0], pp[1] + off[1], pp[2] + off[2], R(0));
-          R ql[4] = {cs * A[0] + sn * B[0], cs * A[1] + sn * B[1], cs * A[2] + sn * B[2], cs * A[3] + sn * B[3]};
-          R q[4]; q_mul(pq, ql, q);
-          // no renormalisation along the chain: the root quaternion is normalised exactly at the top of every FK and
-          // each product of unit quaternions moves |q| by about one ulp, i.e. <= ~12 ulp at the deepest body
-          g_st4(s_xq() + 4 * b, q[0], q[1], q[2], q[3]);
-        }
-      GMR_END
+    GMR_UNROLL
+    for (int k = 0; k < 4; k++) {
+      if ((1 << k) <= dm.maxd) {                                        // a chain of maxd hinges + the root needs 2^K >= maxd + 1
+        GMR_LANES
+          GMR_FK_LOAD
+          if (lane < dm.nh) {
+            const int pb = (int)((mc.fk_idx[lane] >> (8 * k)) & 0xffu);
+            if (pb != 0xff) {
+              R pq[4], pp[4];
+              g_ld4(s_xq() + 4 * pb, pq); g_ld4(s_xp() + 4 * pb, pp);
+              R off[3]; q_rot(pq, p, off);
+              p[0] = pp[0] + off[0]; p[1] = pp[1] + off[1]; p[2] = pp[2] + off[2];
+              R qn[4]; q_mul(pq, q, qn);
+              // no renormalisation along the chain: the root quaternion is normalised exactly at the top of every FK and
+              // each product of unit quaternions moves |q| by about one ulp
+              q[0] = qn[0]; q[1] = qn[1]; q[2] = qn[2]; q[3] = qn[3];
+            }
+          }
+          GMR_FK_SAVE
+        GMR_END
+        GMR_LANES
+          GMR_FK_LOAD
+          if (lane < dm.nh && ((mc.fk_idx[lane] >> (8 * k)) & 0xffu) != 0xff) {
+            const int b = mc.hbody[lane];
+            g_st4(s_xq() + 4 * b, q[0], q[1], q[2], q[3]);
+            g_st4(s_xp() + 4 * b, p[0], p[1], p[2], R(0));
+          }
+        GMR_END
+      }
     }
     GMR_LANES
+      GMR_FK_LOAD
       if (lane < dm.nh) {
-        const int b = mc.hbody[lane];
-        R q[4]; g_ld4(s_xq() + 4 * b, q);
         R w[3]; q_rot(q, mc.axis + 3 * lane, w);
-        R d[4]; g_ld4(s_xp() + 4 * b, d);
         R* o = s_sd() + 8 * lane;
         // linear velocity of the reference point (root origin) under unit joint rate: w x (0 - d) = d x w
-        g_st4(o, d[1] * w[2] - d[2] * w[1], d[2] * w[0] - d[0] * w[2], d[0] * w[1] - d[1] * w[0], w[0]);
+        g_st4(o, p[1] * w[2] - p[2] * w[1], p[2] * w[0] - p[0] * w[2], p[0] * w[1] - p[1] * w[0], w[0]);
         g_st4(o + 4, w[1], w[2], R(0), R(0));
       }
+      for (int e = dm.nh + lane; e < dm.nb - 1; e += 32) {               // fixed bodies: constant pose in a moving body's frame
+        const uint32_t ix = mc.fk_idx[e];
+        const int b = ix & 0xffu, ab = (ix >> 8) & 0xffu;
+        R aq[4], ap[4], C[4], Cp[4];
+        g_ld4(s_xq() + 4 * ab, aq); g_ld4(s_xp() + 4 * ab, ap);
+        g_ld4(mc.fk_A + 4 * e, C); g_ld4(mc.fk_pos + 4 * e, Cp);
+        R off[3]; q_rot(aq, Cp, off);
+        R qf[4]; q_mul(aq, C, qf);
+        g_st4(s_xp() + 4 * b, ap[0] + off[0], ap[1] + off[1], ap[2] + off[2], R(0));
+        g_st4(s_xq() + 4 * b, qf[0], qf[1], qf[2], qf[3]);
+      }
     GMR_END
+#undef GMR_FK_LOAD
+#undef GMR_FK_SAVE
   }
 
   // ------------------------------------------------------------------ targets (A1-A5) ------

@@ -570,44 +570,69 @@ class GeneralMotionRetargeting:
             list(ex.map(one, zip(motions, paths)))
 
 
-def retarget_mixed(buckets, precision: str = "f64", return_info: bool = False):
-    """Mixed-robot batches (BASELINE.json configs[4]) in ONE launch: `buckets` is a list of
-    ``(retargeter, pos [C,T,nh,3], quat [C,T,nh,4], heights [C] or None)`` with torch CUDA tensors on one device, one
-    entry per robot (group the clips with `sharding.bucket_by_robot`).  The device's SMs are divided among the
-    buckets by work, so a bucket's slow clips overlap the other buckets' bulk instead of every bucket paying its own
-    tail.  Each clip is solved exactly as by `retargeter.retarget_batch`.  Returns the list of qpos tensors
-    ([C,T,nq] float32), with `return_info` also the per-frame iteration counts."""
+def retarget_mixed(buckets, precision: str = "f64", return_info: bool = False, device=None):
+    """Mixed-robot batches (BASELINE.json configs[4]) in ONE call: `buckets` is a list of
+    ``(retargeter, pos [C,T,nh,3], quat [C,T,nh,4], heights [C] or None)``, one entry per robot (group the clips with
+    `sharding.bucket_by_robot`).  The arrays are torch CUDA tensors on one device, or torch CPU tensors in PINNED memory
+    (``.pin_memory()``): those are used in place - the kernels read the keypoints over the host link and write qpos
+    into pinned output tensors - and the call returns when the outputs are complete.  The device's SMs are divided
+    among the buckets by work, so a bucket's slow clips overlap the other buckets' bulk instead of every bucket paying
+    its own tail.  Each clip is solved exactly as by `retargeter.retarget_batch`.  Returns the list of qpos tensors
+    ([C,T,nq] float32, on the inputs' side), with `return_info` also the per-frame iteration counts."""
     import torch
     if precision not in ("f32", "f64"):
         raise ValueError("precision must be 'f32' or 'f64'")
     if not buckets:
         return []
     lib = buckets[0][0]._lib
-    dev = buckets[0][1].device
+    p0 = buckets[0][1]
+    if not _is_torch(p0):
+        raise ValueError("retarget_mixed takes torch tensors (CUDA, or CPU in pinned memory)")
+    host = not p0.is_cuda
+    if host:
+        dev = torch.device("cuda", GeneralMotionRetargeting._resolve_device(device if device is not None else buckets[0][0]._device))
+    else:
+        dev = p0.device
     descs = (_native.GmrBatchDesc * len(buckets))()
     keep, outs, iters = [], [], []
     with torch.cuda.device(dev):
         for k, (g, pos, quat, heights) in enumerate(buckets):
-            if not (_is_torch(pos) and pos.is_cuda and pos.device == dev):
-                raise ValueError("retarget_mixed takes torch CUDA tensors on one device")
+            if not (_is_torch(pos) and _is_torch(quat)):
+                raise ValueError("retarget_mixed takes torch tensors")
+            if host:
+                if pos.is_cuda or quat.is_cuda or not (pos.is_pinned() and quat.is_pinned()):
+                    raise ValueError(f"bucket {k}: host buckets must be CPU tensors in pinned memory (.pin_memory())")
+            elif not (pos.is_cuda and pos.device == dev and quat.is_cuda and quat.device == dev):
+                raise ValueError("retarget_mixed takes all buckets on one device")
             nq, nh = g._robot.nq, g._table.nh
             Cn, T = int(pos.shape[0]), int(pos.shape[1])
             if tuple(pos.shape[2:]) != (nh, 3) or tuple(quat.shape) != (Cn, T, nh, 4):
                 raise ValueError(f"bucket {k}: expected pos [C,T,{nh},3] and quat [C,T,{nh},4]")
-            d_pos = pos.to(torch.float32).contiguous(); d_quat = quat.to(dev, torch.float32).contiguous()
+            if pos.dtype != torch.float32 or quat.dtype != torch.float32 or not pos.is_contiguous() or not quat.is_contiguous():
+                if host:
+                    raise ValueError(f"bucket {k}: pinned host buckets must be contiguous float32")
+                pos = pos.to(torch.float32).contiguous(); quat = quat.to(torch.float32).contiguous()
             if heights is None:
                 d_ratio = torch.full((Cn,), g._ratio, dtype=torch.float32, device=dev)
             else:
-                d_ratio = (torch.as_tensor(heights, device=dev).to(torch.float64) / float(g._cfg.human_height_assumption)).to(torch.float32).contiguous()
-            d_q = torch.empty((Cn, T, nq), dtype=torch.float32, device=dev)
-            d_it = torch.zeros((Cn, T, 2), dtype=torch.int32, device=dev) if return_info else None
+                d_ratio = (torch.as_tensor(heights).to(dev).to(torch.float64) / float(g._cfg.human_height_assumption)).to(torch.float32).contiguous()
+            if host:
+                d_q = torch.empty((Cn, T, nq), dtype=torch.float32).pin_memory()
+                d_it = torch.zeros((Cn, T, 2), dtype=torch.int32).pin_memory() if return_info else None
+            else:
+                d_q = torch.empty((Cn, T, nq), dtype=torch.float32, device=dev)
+                d_it = torch.zeros((Cn, T, 2), dtype=torch.int32, device=dev) if return_info else None
             h = g._handle(dev.index if dev.index is not None else torch.cuda.current_device())
-            keep += [d_pos, d_quat, d_ratio, h]
-            descs[k] = _native.GmrBatchDesc(h.ptr.value, d_pos.data_ptr(), d_quat.data_ptr(), d_ratio.data_ptr(), Cn, T, None,
+            keep += [pos, quat, d_ratio, h]
+            # pinned host memory is addressable by the device at the same address (unified virtual addressing)
+            descs[k] = _native.GmrBatchDesc(h.ptr.value, pos.data_ptr(), quat.data_ptr(), d_ratio.data_ptr(), Cn, T, None,
                                             d_q.data_ptr(), None if d_it is None else d_it.data_ptr(), None)
             outs.append(d_q); iters.append(d_it)
         flags = FLAG_COMPUTE_F64 if precision == "f64" else 0
-        rc = lib.gmr_retarget_multi(descs, len(buckets), flags, torch.cuda.current_stream(dev).cuda_stream)
+        stream = torch.cuda.current_stream(dev)
+        rc = lib.gmr_retarget_multi(descs, len(buckets), flags, stream.cuda_stream)
         if rc != 0:
             raise RuntimeError(f"gmr_retarget_multi failed ({rc}): {lib.gmr_last_error().decode()}")
+        if host:
+            stream.synchronize()
     return (outs, iters) if return_info else outs

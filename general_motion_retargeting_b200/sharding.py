@@ -1,10 +1,19 @@
 """Clip sharding for multi-GPU runs: clips are independent (the reference runs one clip per
-pool worker, scripts/smplx_to_robot_dataset.py:241-242), so rank r of W owns a contiguous
-range of clips and there is no collective on the solve path.  Only the timing / result
-hand-over of a caller needs communication (max over ranks, optional gather)."""
+pool worker, scripts/smplx_to_robot_dataset.py:241-242), so every rank owns a set of clips and
+there is no collective on the solve path.  Only the timing / result hand-over of a caller needs
+communication (max over ranks, optional gather).
+
+Two assignments: contiguous ranges (`clip_shard`), and a hardness-aware deal (`lpt_shard`): a
+step ends when the slowest rank ends, and what makes a rank slow is how many HARD clips it drew
+(clips that start far from the robot's initial orientation settle on joint limits and need 2-3x
+the IK steps, DESIGN.md "Clip scheduling"), so the clips are dealt to the ranks in order of a
+cheap hardness proxy - every rank gets the same number of clips and the same share of the hard
+ones."""
 from __future__ import annotations
 
-from typing import List, Tuple
+from typing import List, Sequence, Tuple
+
+import numpy as np
 
 
 def clip_shard(num_clips: int, rank: int, world: int) -> Tuple[int, int]:
@@ -18,6 +27,33 @@ def clip_shard(num_clips: int, rank: int, world: int) -> Tuple[int, int]:
 
 def all_shards(num_clips: int, world: int) -> List[Tuple[int, int]]:
     return [clip_shard(num_clips, r, world) for r in range(world)]
+
+
+def hardness_proxy(quat0: np.ndarray, human_root: int, root_rot_offset: Sequence[float], qpos0_quat: Sequence[float]) -> np.ndarray:
+    """Rotation angle (rad) between each clip's first root target and the robot's initial root orientation - the
+    criterion the library's own clip ordering uses (gmr_order_kernel, csrc/gmr_kernels.cu).  quat0 [C,nh,4] wxyz: frame 0."""
+    q = np.asarray(quat0, np.float64)[:, human_root]
+    o = np.asarray(root_rot_offset, np.float64)
+    a0, a1, a2, a3 = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    t = np.stack([a0 * o[0] - a1 * o[1] - a2 * o[2] - a3 * o[3], a0 * o[1] + a1 * o[0] + a2 * o[3] - a3 * o[2],
+                  a0 * o[2] - a1 * o[3] + a2 * o[0] + a3 * o[1], a0 * o[3] + a1 * o[2] - a2 * o[1] + a3 * o[0]], -1)
+    r = np.asarray(qpos0_quat, np.float64)
+    dot = np.abs(t @ r) / np.maximum(np.linalg.norm(t, axis=-1) * np.linalg.norm(r), 1e-30)
+    return 2.0 * np.arccos(np.clip(dot, 0.0, 1.0))
+
+
+def lpt_shard(hardness: Sequence[float], world: int) -> List[np.ndarray]:
+    """Deal clips to `world` ranks in decreasing order of `hardness`, boustrophedon (0..W-1, W-1..0, ...): every rank gets
+    floor/ceil(C / W) clips and an equal share of every hardness band.  Returns one ascending index array per rank;
+    deterministic (ties broken by clip index), so every rank can compute the same assignment without communication."""
+    h = np.asarray(hardness, np.float64)
+    if world < 1:
+        raise ValueError("bad world size")
+    order = np.lexsort((np.arange(h.size), -h))
+    pos = np.arange(h.size)
+    rnd, k = pos // world, pos % world
+    rank_of = np.where(rnd % 2 == 0, k, world - 1 - k)
+    return [np.sort(order[rank_of == r]) for r in range(world)]
 
 
 def bucket_by_robot(robot_of_clip) -> dict:

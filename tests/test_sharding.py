@@ -31,6 +31,29 @@ def test_bucket_by_robot_groups_and_preserves_order():
     assert b["g1"] == [0, 5, 10, 15, 20] and b["pm01"] == [4, 9, 14, 19]
 
 
+def test_lpt_shard_balances_counts_and_hard_clips():
+    from general_motion_retargeting_b200.sharding import hardness_proxy, lpt_shard
+    rng = np.random.default_rng(3)
+    for C, W in ((4096, 8), (65536, 4), (1001, 3), (5, 8), (0, 2)):
+        h = rng.uniform(0, np.pi, C)
+        sh = lpt_shard(h, W)
+        allidx = np.concatenate(sh) if C else np.zeros(0, int)
+        assert sorted(allidx.tolist()) == list(range(C))                       # a partition
+        sizes = [len(x) for x in sh]
+        assert max(sizes) - min(sizes) <= 1
+        if C >= 1000:
+            hard = [int((h[x] > 2.3).sum()) for x in sh]                       # the library's own "hard clip" band
+            assert max(hard) - min(hard) <= 1
+            assert max(h[x].sum() for x in sh) - min(h[x].sum() for x in sh) < 0.01 * h.sum() / W + np.pi
+    # deterministic, ties by index
+    assert [x.tolist() for x in lpt_shard([1.0, 1.0, 1.0, 1.0], 2)] == [[0, 3], [1, 2]]
+    # the proxy is the rotation angle between root target and initial orientation
+    q = np.zeros((3, 2, 4)); q[:, :, 0] = 1.0
+    q[1, 1] = [np.cos(0.5), 0, 0, np.sin(0.5)]; q[2, 1] = [-np.cos(1.2), 0, -np.sin(1.2), 0]
+    ang = hardness_proxy(q, 1, [1, 0, 0, 0], [1, 0, 0, 0])
+    assert np.allclose(ang, [0.0, 1.0, 2.4], atol=1e-12)
+
+
 WORKER = r'''
 import os, sys
 sys.path.insert(0, os.environ["GMR_ROOT"]); sys.path.insert(0, os.path.join(os.environ["GMR_ROOT"], "tests"))
@@ -69,3 +92,24 @@ def test_two_ranks_over_gloo_equal_one_process(built, tmp_path):
     clips = make_clips(m, tt, range(5), T=6)
     q, *_ = emu_retarget_batch(m, tt, clips.pos, clips.quat, clips.ratio(tt), bits=64)
     np.testing.assert_array_equal(np.load(out), q)
+
+
+def test_dataset_plan_deals_every_bucket_over_the_devices():
+    """dataset.plan_shards: the host logic of the one-process / all-GPUs entry (no GPU needed)."""
+    from helpers import problem
+    from general_motion_retargeting_b200.dataset import plan_shards
+    from general_motion_retargeting_b200.synthetic import make_clips
+    jobs = []
+    for src, robot, n in (("smplx", "unitree_g1", 41), ("bvh", "booster_t1", 7), ("smplx", "engineai_pm01", 0)):
+        m, tt, _ = problem(src, robot)
+        c = make_clips(m, tt, range(n), T=2, src_human=src)
+        jobs.append((src, robot, c.pos, c.quat, c.heights))
+    for W in (1, 2, 8):
+        for shard in ("lpt", "contiguous"):
+            plans = plan_shards(jobs, W, shard)
+            assert len(plans) == 3 and all(len(p) == W for p in plans)
+            for p, (_, _, pos, _, _) in zip(plans, jobs):
+                assert sorted(np.concatenate(p).tolist()) == list(range(pos.shape[0]))
+                assert max(len(x) for x in p) - min(len(x) for x in p) <= 1
+    with pytest.raises(ValueError):
+        plan_shards(jobs, 2, "random")

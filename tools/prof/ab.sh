@@ -1,5 +1,9 @@
-# same-box A/B of two builds of the library: tools/prof/ab.sh (expects csrc/libgmr_old.so next to libgmr_b200.so)
-for lib in libgmr_old.so libgmr_b200.so libgmr_old.so libgmr_b200.so; do
-  echo "== $lib"
-  GMR_B200_LIB=$PWD/general_motion_retargeting_b200/csrc/$lib python tools/prof/latency_probe.py 2>/dev/null | python tools/prof/fmt_probe.py | grep -E "(lone_warp|balanced_all|bench)"
+#!/bin/bash
+# Same-box A/B of library builds on the benchmark mix: tools/prof/ab.sh libA.so libB.so ...   (files under csrc/; each is
+# measured twice, interleaved, PROBE_T=300 unless set)
+export PROBE_T=${PROBE_T:-300}
+for rep in 1 2; do
+  for lib in "$@"; do
+    echo "== $lib $(GMR_B200_LIB=$PWD/general_motion_retargeting_b200/csrc/$lib python tools/prof/mix_case.py ${AB_PREC:-f64 f32} 2>&1 | tail -1)"
+  done
 done
