@@ -24,6 +24,7 @@
 #include "gmr_producers.cuh"
 
 #define GMR_FLAG_INTERNAL_CONVOY 0x80000000u   // set by launch(), never by callers
+#define GMR_FLAG_INTERNAL_NOSTEAL 0x40000000u  // experiment knob (GMR_NO_STEAL=1): dense SMs never take slow clips
 
 
 namespace {
@@ -105,8 +106,17 @@ gmr_order_kernel(const GmrConsts<R>* __restrict__ mc, const float* __restrict__ 
 // ring at a time, so a ring never holds more than C entries; with cap = 2 C + 2 an entry could only be overwritten before its
 // claimant reads it if C + 1 further tickets were claimed in between.
 enum { SQ_AVAIL_N = 0, SQ_NSLOW0 = 1, SQ_NNORM0 = 2, SQ_AVAIL_S = 3, SQ_RES_N = 4, SQ_HEAD_N = 5, SQ_RES_S = 6, SQ_HEAD_S = 7,
-       SQ_DONE = 8, SQ_IDLE_STEAL = 9, SQ_INTS = 16 };
+       SQ_DONE = 8, SQ_IDLE_STEAL = 9, SQ_LIVE_SLOW = 10 /* slow clips alive, relative to n_slow0 */, SQ_INTS = 16 };
 __device__ __forceinline__ int ldv(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+// sparse part of the grid: part_w warps on each of the first b_slow CTAs, at most part_pct % of the CTAs (then more warps each)
+__device__ __forceinline__ void sched_geometry(int n_s0, int part_w, int part_pct, int grid, int wpc, int* pw_out, int* b_slow_out) {
+  int pw = part_w;
+  const int max_blocks = grid * part_pct / 100;
+  if (max_blocks > 0 && (n_s0 + pw - 1) / pw > max_blocks) pw = (n_s0 + max_blocks - 1) / max_blocks;
+  if (pw > wpc) pw = wpc;
+  *pw_out = pw;
+  *b_slow_out = (n_s0 + pw - 1) / pw < max_blocks ? (n_s0 + pw - 1) / pw : max_blocks;
+}
 __device__ __forceinline__ int sq_pop(int* q, const long long* ring, int cap, int avail_i, int head_i, int n0) {
   if (n0 + ldv(q + avail_i) <= 0) return -1;                          // cheap look before touching the counter
   if (n0 + atomicSub(q + avail_i, 1) <= 0) { atomicAdd(q + avail_i, 1); return -1; }
@@ -186,18 +196,17 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
   // Pure scheduling: a clip's frames are solved in order from its own state, whichever warps run its segments.
   // Nothing of the scheduler stays in registers across a segment (the solver needs all of them): the warp's role, what it
   // is running and the clip id live in two spare words next to the warp's mbarrier and are re-read between segments.
-  enum { W_SLOW_BLOCK = 1, W_STEALER = 2, W_TOOK_SLOW = 4, W_COUNTED_IDLE = 8, W_HAVE = 16 };
+  enum { W_SLOW_BLOCK = 1, W_STEALER = 2, W_TOOK_SLOW = 4, W_COUNTED_IDLE = 8, W_HAVE = 16, W_SPARE = 32 };
   volatile int* const wword = reinterpret_cast<volatile int*>(reinterpret_cast<unsigned char*>(ws.s_bar()) + 8);   // [0] role bits, [1] clip
+  int* const n_res = reinterpret_cast<int*>(smem + 12);               // slow clips resident on this (sparse) SM
   if (part_w > 0) {
-    const int n_s0 = queue[SQ_NSLOW0];
-    int pw = part_w;
-    const int max_blocks = (int)gridDim.x * part_pct / 100;           // at most this share of the SMs goes sparse
-    if (max_blocks > 0 && (n_s0 + pw - 1) / pw > max_blocks) pw = (n_s0 + max_blocks - 1) / max_blocks;
-    if (pw > wpc) pw = wpc;
-    const int b_slow = (n_s0 + pw - 1) / pw < max_blocks ? (n_s0 + pw - 1) / pw : max_blocks;
+    if (threadIdx.x == 0) *n_res = 0;
+    __syncthreads();
+    int pw, b_slow;
+    sched_geometry(queue[SQ_NSLOW0], part_w, part_pct, (int)gridDim.x, wpc, &pw, &b_slow);
     const bool slow_block = (int)blockIdx.x < b_slow;
-    if (slow_block && warp >= pw) return;                              // the sparse SMs' spare warps
-    if (lane == 0) wword[0] = slow_block ? W_SLOW_BLOCK : (warp < 4 ? W_STEALER : 0);
+    if (lane == 0) wword[0] = slow_block ? (W_SLOW_BLOCK | (warp >= pw ? W_SPARE : 0))
+                                         : ((warp < 4 && !(kflags & GMR_FLAG_INTERNAL_NOSTEAL)) ? W_STEALER : 0);
     __syncwarp();
   }
   int p = warp * (int)gridDim.x + (int)blockIdx.x;                    // plain launch: position in the clip order
@@ -208,6 +217,7 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
       const int n_hard = order ? queue[1] : 0;                        // queue = {next position, n_hard, n_easy, -}
       c = order ? (p < n_hard ? order[p] : order[C + p - n_hard]) : p;
     } else {
+      int nap = 1000;
       if (lane == 0) {
         int w = wword[0];
         if (w & W_HAVE) c = wword[1];                                  // the clip keeps its warp for another segment
@@ -215,9 +225,29 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
           const int cap = 2 * C + 2;
           const int n_s0 = queue[SQ_NSLOW0], n_n0 = queue[SQ_NNORM0];
           w &= ~W_TOOK_SLOW;
-          if (w & W_SLOW_BLOCK) { c = sq_pop(queue, rings, cap, SQ_AVAIL_S, SQ_HEAD_S, n_s0); if (c >= 0) w |= W_TOOK_SLOW; }
-          if (c < 0) c = sq_pop(queue, rings + cap, cap, SQ_AVAIL_N, SQ_HEAD_N, n_n0);
-          if (c < 0 && (w & W_STEALER)) { c = sq_pop(queue, rings, cap, SQ_AVAIL_S, SQ_HEAD_S, n_s0); if (c >= 0) w |= W_TOOK_SLOW; }
+          if (w & W_SLOW_BLOCK) {
+            // A sparse SM takes slow clips up to its fair share of the ones alive (on its first part_w warps) and nothing else
+            // while it hosts any: a normal clip beside them would cost every slow clip on the SM more than it gains.  With no
+            // slow clip left or waiting, the SM turns dense (all warps, normal ring).
+            const bool waiting = n_s0 + ldv(queue + SQ_AVAIL_S) > 0;
+            const int here = *reinterpret_cast<volatile int*>(n_res);
+            if (!(w & W_SPARE) && waiting) {
+              int pw, b_slow;
+              sched_geometry(n_s0, part_w, part_pct, (int)gridDim.x, wpc, &pw, &b_slow);
+              const int alive = n_s0 + ldv(queue + SQ_LIVE_SLOW);
+              int target = (alive + b_slow - 1) / b_slow;
+              if (target < 1) target = 1;
+              if (here < target) {
+                c = sq_pop(queue, rings, cap, SQ_AVAIL_S, SQ_HEAD_S, n_s0);
+                if (c >= 0) { w |= W_TOOK_SLOW; atomicAdd(n_res, 1); }
+              }
+            }
+            if (c < 0 && here == 0 && !waiting) c = sq_pop(queue, rings + cap, cap, SQ_AVAIL_N, SQ_HEAD_N, n_n0);
+            if (c < 0 && (w & W_SPARE)) nap = 20000;
+          } else {
+            c = sq_pop(queue, rings + cap, cap, SQ_AVAIL_N, SQ_HEAD_N, n_n0);
+            if (c < 0 && (w & W_STEALER)) { c = sq_pop(queue, rings, cap, SQ_AVAIL_S, SQ_HEAD_S, n_s0); if (c >= 0) w |= W_TOOK_SLOW; }
+          }
           if (c < 0) {
             if (ldv(queue + SQ_DONE) >= C) c = -2;
             else if ((w & W_STEALER) && !(w & W_COUNTED_IDLE)) { atomicAdd(queue + SQ_IDLE_STEAL, 1); w |= W_COUNTED_IDLE; }
@@ -230,7 +260,7 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
       }
       c = __shfl_sync(0xffffffffu, c, 0);
       if (c == -2) break;
-      if (c < 0) { __nanosleep(1000); continue; }
+      if (c < 0) { __nanosleep(__shfl_sync(0xffffffffu, nap, 0)); continue; }
       __threadfence();                                                 // the clip's state may have been written by another warp
     }
     const int nt = ws.template run_clip<IO>(io, c, part_w > 0 ? seg_frames : 0);
@@ -247,21 +277,40 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
     if (lane == 0) {
       const int cc = wword[1];
       int w = wword[0];
+      const bool took_slow = (w & W_TOOK_SLOW) != 0, resident = took_slow && (w & W_SLOW_BLOCK);
       int T_c = io.T;
       if (io.ex.lengths) { T_c = io.ex.lengths[cc]; T_c = T_c < 0 ? 0 : (T_c > io.T ? io.T : T_c); }
       if (nt < 0 || nt >= T_c) {                                       // complete (or stopped by a fatal status)
         atomicAdd(queue + SQ_DONE, 1);
+        if (took_slow) atomicSub(queue + SQ_LIVE_SLOW, 1);
+        if (resident) atomicSub(n_res, 1);
         w &= ~W_HAVE;
       } else {
-        // a slow clip keeps its warp, unless it sits on a sparse SM while lone-speed slots are idle elsewhere; a normal
-        // clip keeps its warp while nobody is waiting in the normal ring
-        const bool now_slow = (double)ws.s_piv()[1] > slow_err, took_slow = (w & W_TOOK_SLOW) != 0;
+        const bool now_slow = (double)ws.s_piv()[1] > slow_err;
+        const int n_s0 = queue[SQ_NSLOW0];
         bool keep;
-        if (now_slow) keep = took_slow && !((w & W_SLOW_BLOCK) && ldv(queue + SQ_IDLE_STEAL) > 0);
-        else keep = !took_slow && queue[SQ_NNORM0] + ldv(queue + SQ_AVAIL_N) <= 0;
+        if (now_slow && took_slow) {
+          // a slow clip keeps its warp, unless it sits on a sparse SM that holds more than its fair share of the slow clips
+          // alive, or lone-speed slots are idle elsewhere
+          keep = true;
+          if (resident) {
+            int pw, b_slow;
+            sched_geometry(n_s0, part_w, part_pct, (int)gridDim.x, wpc, &pw, &b_slow);
+            const int alive = n_s0 + ldv(queue + SQ_LIVE_SLOW);
+            int target = (alive + b_slow - 1) / b_slow;
+            if (target < 1) target = 1;
+            keep = !(ldv(queue + SQ_IDLE_STEAL) > 0 || *reinterpret_cast<volatile int*>(n_res) > target);
+          }
+        } else if (!now_slow && !took_slow) {
+          // a normal clip keeps its warp while nobody is waiting in the normal ring - except on a sparse SM that has slow work again
+          keep = queue[SQ_NNORM0] + ldv(queue + SQ_AVAIL_N) <= 0 &&
+                 !((w & W_SLOW_BLOCK) && (*reinterpret_cast<volatile int*>(n_res) > 0 || n_s0 + ldv(queue + SQ_AVAIL_S) > 0));
+        } else keep = false;                                           // the clip changes class
         if (!keep) {
           const int cap = 2 * C + 2;
-          if (now_slow) sq_push(queue, rings, cap, SQ_AVAIL_S, SQ_RES_S, queue[SQ_NSLOW0], cc);
+          if (resident) atomicSub(n_res, 1);
+          if (now_slow != took_slow) atomicAdd(queue + SQ_LIVE_SLOW, now_slow ? 1 : -1);
+          if (now_slow) sq_push(queue, rings, cap, SQ_AVAIL_S, SQ_RES_S, n_s0, cc);
           else sq_push(queue, rings + cap, cap, SQ_AVAIL_N, SQ_RES_N, queue[SQ_NNORM0], cc);
           w &= ~W_HAVE;
           act = now_slow && took_slow;
@@ -269,7 +318,7 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
       }
       wword[0] = w;
     }
-    if (__shfl_sync(0xffffffffu, act, 0)) __nanosleep(4000);           // let the idle lone-speed slot win the pop
+    if (__shfl_sync(0xffffffffu, act, 0)) __nanosleep(4000);           // let the slot that should take it win the pop
   }
   ws.convoy_retire();
 }
@@ -430,7 +479,7 @@ template <typename R> int pick_wpc(const GmrModel* m, int C, int sms = 0) {
   while (wpc > 1 && smem_bytes<R>(m, wpc) > (size_t)m->max_smem) wpc--;
   int need = (C + sms * ctas_per_sm() - 1) / (sms * ctas_per_sm());
   if (need < 1) need = 1;
-  if (need < wpc) wpc = need;
+  if (need < wpc && !getenv("GMR_WPC_FULL")) wpc = need;                 // GMR_WPC_FULL: experiment knob, always the full CTA
   return wpc;
 }
 
@@ -461,7 +510,9 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
   // mixed ones (a slow clip no longer drags its CTA through a rendezvous per factorisation).  GMR_CONVOY=1 re-enables.
   static const int cv_env = getenv("GMR_CONVOY") ? atoi(getenv("GMR_CONVOY")) : 0;
   const bool convoy = cv_env != 0 && wpc >= 2;
-  flags = (flags & 0xffffu) | (convoy ? GMR_FLAG_INTERNAL_CONVOY : 0u);
+  static const int nosteal_env = getenv("GMR_NO_STEAL") ? atoi(getenv("GMR_NO_STEAL")) : 0;
+  static const int force_sched_env = getenv("GMR_FORCE_SCHED") ? atoi(getenv("GMR_FORCE_SCHED")) : 0;
+  flags = (flags & 0xffffu) | (convoy ? GMR_FLAG_INTERNAL_CONVOY : 0u) | (nosteal_env ? GMR_FLAG_INTERNAL_NOSTEAL : 0u);
   GmrIO<IO> io{};
   io.pos = pos; io.quat = quat; io.ratio = ratio; io.qinit = qinit; io.qout = qout; io.iters = iters; io.err = err; io.tg = tg;
   io.C = C; io.T = T; io.flags = flags & 0xffffu; io.ex = ex; io.trace = g_trace.load();
@@ -482,7 +533,7 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
   static const int seg_env = getenv("GMR_SEGMENT") ? atoi(getenv("GMR_SEGMENT")) : 25;
   static const double slow_err_env = getenv("GMR_SLOW_ERR") ? atof(getenv("GMR_SLOW_ERR")) : 1.0;
   const bool two_phase = part_env > 0 && seg_env > 0 && !own_queue && !convoy && !(flags & GMR_FLAG_NO_SOLVE) && T >= 16 &&
-                         C > 2 * sms * part_env;
+                         (C > 2 * sms * part_env || force_sched_env);
   if (two_phase) {
     const int stride = gmr_state_stride(dims.nq), cap = 2 * C + 2;
     const size_t b_state = ((size_t)C * stride * sizeof(double) + 255) & ~(size_t)255, b_ring = (size_t)2 * cap * sizeof(long long);

@@ -347,7 +347,7 @@ template <typename IO> struct GmrIO {
   // clip from one launch - or one SEGMENT of the scheduled launch, see run_clip - to the next at full precision
   int32_t t_begin, t_end;
   double* state;
-  // profiling aid (gmr_debug_trace): [2C,4] int64 {start ns, end ns, sm | warp << 16, factorisations} per clip;
+  // profiling aid (gmr_debug_trace): [2C,4] int64 {first start ns, last end ns, running ns, factorisations | segments << 32 | last SM << 48} per clip;
   // rows [0, C) are written by launches that start at frame 0, rows [C, 2C) by launches that continue a clip
   long long* trace;
 };
@@ -1436,8 +1436,10 @@ struct WarpSolver {
     stat_refactor = 0;
 #ifndef GMR_EMULATE
     if (io.trace && lane_ == 0) {                                     // nothing of the trace stays live across the clip
-      long long* o = io.trace + 4 * ((size_t)(tb > 0 ? io.C : 0) + c);
-      if (seg_frames == 0 || g_ldcg(o) == 0) { long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0)); o[0] = t0; o[3] = 0; }
+      long long* o = io.trace + 4 * ((size_t)(io.t_begin > 0 ? io.C : 0) + c);
+      long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      if (seg_frames == 0 || g_ldcg(o) == 0) { o[0] = t0; o[2] = 0; o[3] = 0; }
+      o[1] = t0;                                                      // start of this segment (overwritten by its end below)
     }
 #endif
     int stat_frame = -1;                                              // frame of the first status event
@@ -1571,12 +1573,14 @@ struct WarpSolver {
     }
 #ifndef GMR_EMULATE
     if (io.trace && lane_ == 0) {
-      long long t1; unsigned smid;
+      long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      const unsigned smid = blockIdx.x;                                // the CTA (one per SM): tells sparse from dense SMs
       long long* o = io.trace + 4 * ((size_t)(io.t_begin > 0 ? io.C : 0) + c);
-      o[1] = t1; o[2] = (long long)(smid | ((threadIdx.x >> 5) << 16));
-      o[3] = g_ldcg(o + 3) + (long long)stat_refactor;                   // segments of one clip accumulate into one row
+      // segments of one clip accumulate into one row: running time, factorisations | segments << 32 | last SM << 48
+      o[2] = g_ldcg(o + 2) + (t1 - g_ldcg(o + 1));
+      o[1] = t1;
+      o[3] = ((g_ldcg(o + 3) & 0xffffffffffffll) + (long long)stat_refactor + (1ll << 32)) | ((long long)smid << 48);
     }
 #endif
     const bool stopped = (stat_flags & GMR_STATUS_FATAL) != 0;
