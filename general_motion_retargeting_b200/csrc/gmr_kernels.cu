@@ -106,16 +106,33 @@ gmr_order_kernel(const GmrConsts<R>* __restrict__ mc, const float* __restrict__ 
 // ring at a time, so a ring never holds more than C entries; with cap = 2 C + 2 an entry could only be overwritten before its
 // claimant reads it if C + 1 further tickets were claimed in between.
 enum { SQ_AVAIL_N = 0, SQ_NSLOW0 = 1, SQ_NNORM0 = 2, SQ_AVAIL_S = 3, SQ_RES_N = 4, SQ_HEAD_N = 5, SQ_RES_S = 6, SQ_HEAD_S = 7,
-       SQ_DONE = 8, SQ_IDLE_STEAL = 9, SQ_LIVE_SLOW = 10 /* slow clips alive, relative to n_slow0 */, SQ_INTS = 16 };
+       SQ_DONE = 8, SQ_IDLE_STEAL = 9, SQ_LIVE_SLOW = 10 /* slow clips alive, relative to n_slow0 */,
+       SQ_FR_NORM = 12 /* frames solved so far by clips taken as normal */, SQ_INTS = 16 };
 __device__ __forceinline__ int ldv(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
-// sparse part of the grid: part_w warps on each of the first b_slow CTAs, at most part_pct % of the CTAs (then more warps each)
+// Is a slow clip on the batch's critical path?  It is when it lags the normal class, measured in frames solved (every clip of
+// a batch has about the same number of frames): t frames of its own against fn / nn frames per normal clip - such a clip will
+// still be running when the bulk is done, so every microsecond it loses to a neighbour is lost for the batch, and its SM stays
+// exclusive.  A slow clip that is ahead of the bulk (many waves of normal clips per warp slot) can share its SM: the bulk, not
+// the clip, ends the batch.  "Critical" until the normal class has reported progress; never when there is no normal class to
+// speak of (under an eighth of the clips: then the slow clips ARE the bulk and throughput is all that counts).
+__device__ __forceinline__ bool no_normal_class(const int* q) {
+  const long long nn = q[SQ_NNORM0] - ldv(q + SQ_LIVE_SLOW), ns = q[SQ_NSLOW0] + ldv(q + SQ_LIVE_SLOW);
+  return 8 * nn < ns;
+}
+__device__ __forceinline__ bool slow_clip_critical(const int* q, int t_done) {
+  const long long fn = ldv(q + SQ_FR_NORM), nn = q[SQ_NNORM0] - ldv(q + SQ_LIVE_SLOW);
+  if (no_normal_class(q)) return false;
+  if (fn <= 0) return true;
+  return (long long)t_done * nn < fn;
+}
+// Sparse part of the grid: part_w warps on each of the first b_slow CTAs.  When the suspects do not fit into part_pct % of
+// the SMs at part_w per SM, there is no sparse part at all (b_slow = 0): so many slow clips are not a tail to protect but a
+// large share of the work, and every SM serves both rings at full occupancy, slow clips first.
 __device__ __forceinline__ void sched_geometry(int n_s0, int part_w, int part_pct, int grid, int wpc, int* pw_out, int* b_slow_out) {
-  int pw = part_w;
-  const int max_blocks = grid * part_pct / 100;
-  if (max_blocks > 0 && (n_s0 + pw - 1) / pw > max_blocks) pw = (n_s0 + max_blocks - 1) / max_blocks;
-  if (pw > wpc) pw = wpc;
+  const int pw = part_w < wpc ? part_w : wpc;
+  const int max_blocks = grid * part_pct / 100, need = (n_s0 + pw - 1) / pw;
   *pw_out = pw;
-  *b_slow_out = (n_s0 + pw - 1) / pw < max_blocks ? (n_s0 + pw - 1) / pw : max_blocks;
+  *b_slow_out = need <= max_blocks ? need : 0;
 }
 __device__ __forceinline__ int sq_pop(int* q, const long long* ring, int cap, int avail_i, int head_i, int n0) {
   if (n0 + ldv(q + avail_i) <= 0) return -1;                          // cheap look before touching the counter
@@ -196,11 +213,12 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
   // Pure scheduling: a clip's frames are solved in order from its own state, whichever warps run its segments.
   // Nothing of the scheduler stays in registers across a segment (the solver needs all of them): the warp's role, what it
   // is running and the clip id live in two spare words next to the warp's mbarrier and are re-read between segments.
-  enum { W_SLOW_BLOCK = 1, W_STEALER = 2, W_TOOK_SLOW = 4, W_COUNTED_IDLE = 8, W_HAVE = 16, W_SPARE = 32 };
+  enum { W_SLOW_BLOCK = 1, W_STEALER = 2, W_TOOK_SLOW = 4, W_COUNTED_IDLE = 8, W_HAVE = 16, W_SPARE = 32, W_CRITICAL = 64 };
   volatile int* const wword = reinterpret_cast<volatile int*>(reinterpret_cast<unsigned char*>(ws.s_bar()) + 8);   // [0] role bits, [1] clip
   int* const n_res = reinterpret_cast<int*>(smem + 12);               // slow clips resident on this (sparse) SM
+  int* const n_crit = reinterpret_cast<int*>(smem + 4);               // ... of which on the critical path (the constants' mbarrier is dead by now)
   if (part_w > 0) {
-    if (threadIdx.x == 0) *n_res = 0;
+    if (threadIdx.x == 0) { *n_res = 0; *n_crit = 0; }
     __syncthreads();
     int pw, b_slow;
     sched_geometry(queue[SQ_NSLOW0], part_w, part_pct, (int)gridDim.x, wpc, &pw, &b_slow);
@@ -239,14 +257,24 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
               if (target < 1) target = 1;
               if (here < target) {
                 c = sq_pop(queue, rings, cap, SQ_AVAIL_S, SQ_HEAD_S, n_s0);
-                if (c >= 0) { w |= W_TOOK_SLOW; atomicAdd(n_res, 1); }
+                if (c >= 0) { w |= W_TOOK_SLOW | W_CRITICAL; atomicAdd(n_res, 1); atomicAdd(n_crit, 1); }
               }
             }
-            if (c < 0 && here == 0 && !waiting) c = sq_pop(queue, rings + cap, cap, SQ_AVAIL_N, SQ_HEAD_N, n_n0);
+            if (c < 0 && ((here == 0 && !waiting) || *reinterpret_cast<volatile int*>(n_crit) == 0))
+              c = sq_pop(queue, rings + cap, cap, SQ_AVAIL_N, SQ_HEAD_N, n_n0);
             if (c < 0 && (w & W_SPARE)) nap = 20000;
           } else {
-            c = sq_pop(queue, rings + cap, cap, SQ_AVAIL_N, SQ_HEAD_N, n_n0);
-            if (c < 0 && (w & W_STEALER)) { c = sq_pop(queue, rings, cap, SQ_AVAIL_S, SQ_HEAD_S, n_s0); if (c >= 0) w |= W_TOOK_SLOW; }
+            int pw_, b_slow_;
+            sched_geometry(n_s0, part_w, part_pct, (int)gridDim.x, wpc, &pw_, &b_slow_);
+            if (b_slow_ == 0 && n_s0 > 0) {                            // no sparse part: slow clips first, on any warp
+              c = sq_pop(queue, rings, cap, SQ_AVAIL_S, SQ_HEAD_S, n_s0); if (c >= 0) w |= W_TOOK_SLOW;
+            }
+            if (c < 0) c = sq_pop(queue, rings + cap, cap, SQ_AVAIL_N, SQ_HEAD_N, n_n0);
+            // out of normal clips: one warp per scheduler takes a slow clip (lone-warp speed); every warp does when slow
+            // clips are queueing for want of sparse capacity (more than one per sparse SM waiting) or are the bulk themselves
+            if (c < 0 && ((w & W_STEALER) || n_s0 + ldv(queue + SQ_AVAIL_S) > (int)gridDim.x / 2 || no_normal_class(queue))) {
+              c = sq_pop(queue, rings, cap, SQ_AVAIL_S, SQ_HEAD_S, n_s0); if (c >= 0) w |= W_TOOK_SLOW;
+            }
           }
           if (c < 0) {
             if (ldv(queue + SQ_DONE) >= C) c = -2;
@@ -278,13 +306,18 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
       const int cc = wword[1];
       int w = wword[0];
       const bool took_slow = (w & W_TOOK_SLOW) != 0, resident = took_slow && (w & W_SLOW_BLOCK);
+      if (!took_slow) atomicAdd(queue + SQ_FR_NORM, seg_frames);
+      if (resident) {                                                  // refresh this clip's "critical" mark
+        const bool crit = nt >= 0 && slow_clip_critical(queue, nt);
+        if (crit != ((w & W_CRITICAL) != 0)) { atomicAdd(n_crit, crit ? 1 : -1); w ^= W_CRITICAL; }
+      }
       int T_c = io.T;
       if (io.ex.lengths) { T_c = io.ex.lengths[cc]; T_c = T_c < 0 ? 0 : (T_c > io.T ? io.T : T_c); }
       if (nt < 0 || nt >= T_c) {                                       // complete (or stopped by a fatal status)
         atomicAdd(queue + SQ_DONE, 1);
         if (took_slow) atomicSub(queue + SQ_LIVE_SLOW, 1);
-        if (resident) atomicSub(n_res, 1);
-        w &= ~W_HAVE;
+        if (resident) { atomicSub(n_res, 1); if (w & W_CRITICAL) atomicSub(n_crit, 1); }
+        w &= ~(W_HAVE | W_CRITICAL);
       } else {
         const bool now_slow = (double)ws.s_piv()[1] > slow_err;
         const int n_s0 = queue[SQ_NSLOW0];
@@ -299,16 +332,17 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
             const int alive = n_s0 + ldv(queue + SQ_LIVE_SLOW);
             int target = (alive + b_slow - 1) / b_slow;
             if (target < 1) target = 1;
-            keep = !(ldv(queue + SQ_IDLE_STEAL) > 0 || *reinterpret_cast<volatile int*>(n_res) > target);
+            keep = !((ldv(queue + SQ_IDLE_STEAL) > 0 && !no_normal_class(queue)) || *reinterpret_cast<volatile int*>(n_res) > target);
           }
         } else if (!now_slow && !took_slow) {
           // a normal clip keeps its warp while nobody is waiting in the normal ring - except on a sparse SM that has slow work again
           keep = queue[SQ_NNORM0] + ldv(queue + SQ_AVAIL_N) <= 0 &&
-                 !((w & W_SLOW_BLOCK) && (*reinterpret_cast<volatile int*>(n_res) > 0 || n_s0 + ldv(queue + SQ_AVAIL_S) > 0));
+                 !((w & W_SLOW_BLOCK) && (*reinterpret_cast<volatile int*>(n_crit) > 0 || n_s0 + ldv(queue + SQ_AVAIL_S) > 0));
         } else keep = false;                                           // the clip changes class
         if (!keep) {
           const int cap = 2 * C + 2;
-          if (resident) atomicSub(n_res, 1);
+          if (resident) { atomicSub(n_res, 1); if (w & W_CRITICAL) atomicSub(n_crit, 1); }
+          w &= ~W_CRITICAL;
           if (now_slow != took_slow) atomicAdd(queue + SQ_LIVE_SLOW, now_slow ? 1 : -1);
           if (now_slow) sq_push(queue, rings, cap, SQ_AVAIL_S, SQ_RES_S, n_s0, cc);
           else sq_push(queue, rings + cap, cap, SQ_AVAIL_N, SQ_RES_N, queue[SQ_NNORM0], cc);

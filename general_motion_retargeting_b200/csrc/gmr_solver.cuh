@@ -42,13 +42,18 @@
 #include <cstring>
 #define GMR_FN inline
 #define GMR_HD inline
-#define GMR_LANES for (int lane = 0; lane < 32; ++lane) { LaneRegs<R>& L = lanes_[lane]; (void)L;
+// The emulator runs the lanes of a block one after the other, in the order gmr_emu_lane_order gives (identity by default).
+// A lane block must not depend on that order - "inside one block a lane never reads shared memory another lane writes in
+// the same block" - so tests/test_emulator.py runs the same clips under reversed and shuffled orders and demands
+// bit-identical results: the CPU stand-in for a racecheck of the blocks' intra-warp hazards.
+static int gmr_emu_lane_order[32] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31};
+#define GMR_LANES for (int li_ = 0; li_ < 32; ++li_) { const int lane = gmr_emu_lane_order[li_]; LaneRegs<R>& L = lanes_[lane]; (void)L;
 #define GMR_END }
 #define GMR_UNROLL
 #define GMR_SYNC()
 // end the lane loop, broadcast per-lane register(s) of lane `src` to every lane, open a new lane loop
-#define GMR_BCAST1(src, f0) } { const R bc0 = lanes_[src].f0; for (int lane = 0; lane < 32; ++lane) { LaneRegs<R>& L = lanes_[lane]; (void)L;
-#define GMR_BCAST2(src, f0, f1) } { const R bc0 = lanes_[src].f0, bc1 = lanes_[src].f1; for (int lane = 0; lane < 32; ++lane) { LaneRegs<R>& L = lanes_[lane]; (void)L;
+#define GMR_BCAST1(src, f0) } { const R bc0 = lanes_[src].f0; for (int li_ = 0; li_ < 32; ++li_) { const int lane = gmr_emu_lane_order[li_]; LaneRegs<R>& L = lanes_[lane]; (void)L;
+#define GMR_BCAST2(src, f0, f1) } { const R bc0 = lanes_[src].f0, bc1 = lanes_[src].f1; for (int li_ = 0; li_ < 32; ++li_) { const int lane = gmr_emu_lane_order[li_]; LaneRegs<R>& L = lanes_[lane]; (void)L;
 #define GMR_END_BCAST } }
 #define GMR_END_BCAST_NOSYNC } }
 #define GMR_END_NOSYNC }
@@ -133,6 +138,16 @@ template <typename R> inline void gmr_dims_layout(GmrDims& d) {
 }
 
 // relative tolerance of the KKT multiplier sign test (the Lie threshold is a model parameter: GmrScal::lie)
+#if defined(GMR_EMULATE) && defined(GMR_STATS)
+// active-set statistics of the emulator build (tools/prof/active_set_stats.py): [0] solves, [1] SOLVE passes (factorisations),
+// [2] passes that ended blocked (a bound added), [3] CHECK passes, [4] checks that released bounds, [5] bounds released,
+// [6] sum of pinned joints at the end of a solve, [7] solves that ended with pins, [8] solves whose warm set was already optimal
+#include <atomic>
+static std::atomic<long long> gmr_stats[16];
+#define GMR_STAT(i, n) gmr_stats[i] += (n)
+#else
+#define GMR_STAT(i, n)
+#endif
 template <typename R> struct GmrEps;
 template <> struct GmrEps<float>  { static constexpr float  lam = 1e-5f;  };
 template <> struct GmrEps<double> { static constexpr double lam = 1e-12; };
@@ -1103,6 +1118,7 @@ struct WarpSolver {
       }
     GMR_END
     uint32_t pin_lo = w_lo & dm.limited_mask, pin_hi = w_hi & dm.limited_mask;
+    GMR_STAT(0, 1);
     int nchecks = 0;
     bool check = false;
     const int max_as = 8 * dm.nh + 16;
@@ -1120,6 +1136,7 @@ struct WarpSolver {
         if (pinned) apply_pins(pinned);
         factor_solve(pinned);
         stat_refactor++;
+        GMR_STAT(1, 1);
         // ratio test towards the candidate
         bool blocked = false;
         GMR_LANES
@@ -1175,6 +1192,7 @@ struct WarpSolver {
           const bool up = s_piv()[2] > R(0);
           GMR_SYNC();
           if (up) pin_hi |= 1u << blk; else pin_lo |= 1u << blk;
+          GMR_STAT(2, 1);
           continue;
         }
         GMR_LANES
@@ -1182,6 +1200,7 @@ struct WarpSolver {
         GMR_END
         if (!pinned) break;
         check = true;
+        GMR_STAT(3, 1);
         continue;
       }
       // CHECK pass: g = H x + c on the original rows (just rebuilt); x is in s_xs.  Every lane publishes
@@ -1240,12 +1259,15 @@ struct WarpSolver {
       if (worst < 0 || lmin >= -GmrEps<R>::lam * gmax) { GMR_SYNC(); break; }
       uint32_t drop = 1u << worst;
       if (nchecks < 2) drop |= drop_all;
+      GMR_STAT(4, 1); GMR_STAT(5, __builtin_popcount(drop));
       nchecks++;
       GMR_SYNC();
       pin_lo &= ~drop; pin_hi &= ~drop;
       check = false;
     }
     if (it >= max_as) stat_flags |= GMR_STATUS_AS_CAP;            // feasible point, optimality not proven
+    GMR_STAT(6, __builtin_popcount(pin_lo | pin_hi)); GMR_STAT(7, (pin_lo | pin_hi) ? 1 : 0);
+    GMR_STAT(8, (pin_lo == (w_lo & dm.limited_mask) && pin_hi == (w_hi & dm.limited_mask)) ? 1 : 0);
     if (stage == 0) { warm_lo0 = pin_lo; warm_hi0 = pin_hi; } else { warm_lo1 = pin_lo; warm_hi1 = pin_hi; }
     // publish the final step (hinge part) for integration
     GMR_LANES

@@ -67,3 +67,17 @@ extern "C" int gmr_emu_retarget_batch_ex(const GmrModelDesc* d, const float* pos
     return run<float>(d, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out, tg_out, flags, nthreads, nullptr, ex);
   return run<double>(d, pos, quat, ratio, C, T, qpos_init, qpos_out, iters_out, err_out, tg_out, flags, nthreads, nullptr, ex);
 }
+
+// order in which the emulator visits the lanes of a block (a permutation of 0..31; not thread safe: set it between runs)
+extern "C" int gmr_emu_set_lane_order(const int* order) {
+  bool seen[32] = {};
+  for (int i = 0; i < 32; i++) { if (order[i] < 0 || order[i] > 31 || seen[order[i]]) return -1; seen[order[i]] = true; }
+  for (int i = 0; i < 32; i++) gmr_emu_lane_order[i] = order[i];
+  return 0;
+}
+
+#ifdef GMR_STATS
+extern "C" void gmr_emu_stats(long long* out, int reset) {
+  for (int i = 0; i < 16; i++) { out[i] = gmr_stats[i].load(); if (reset) gmr_stats[i] = 0; }
+}
+#endif

@@ -179,3 +179,39 @@ def test_compiled_in_limits_are_reported_not_truncated(built, tmp_path):
         assert rc == want, (n, rc)
         if want == 0:
             assert np.isfinite(q).all() and abs(np.linalg.norm(q[0, -1, 3:7]) - 1) < 1e-12
+
+
+@pytest.mark.parametrize("bits", [64, 32])
+def test_lane_blocks_do_not_depend_on_the_lane_order(built, bits):
+    """compute-sanitizer is closed on the GPU pool (profiles/r2_compute_sanitizer_closed.txt), so the intra-warp hazards of the
+    lane blocks are checked here: the emulator visits the 32 lanes of every block in a given order, and the kernel's rule -
+    inside one block a lane never reads shared memory another lane writes in the same block - means the result cannot depend
+    on it.  Normal and stress clips (active sets, several factorisations per solve), FK epilogue and ragged lengths included;
+    identity, reversed and two shuffled orders must agree bit for bit."""
+    import ctypes as C
+    import helpers
+    from helpers import emu_retarget_batch_ex
+    m, tt, _ = problem("smplx", "unitree_g1")
+    a = make_clips(m, tt, range(3), T=10)
+    b = make_clips(m, tt, range(3), T=10, stress=True)
+    pos, quat = np.concatenate([a.pos, b.pos]), np.concatenate([a.quat, b.quat])
+    ratio = np.concatenate([a.ratio(tt), b.ratio(tt)])
+    lengths = np.array([10, 7, 10, 10, 9, 10], np.int32)
+    rng = np.random.default_rng(5)
+    orders = [np.arange(32), np.arange(32)[::-1], rng.permutation(32), rng.permutation(32)]
+    results = []
+    try:
+        for o in orders:
+            emu_retarget_batch(m, tt, pos[:1], quat[:1], ratio[:1], bits=bits)          # makes sure the library is loaded
+            arr = (C.c_int * 32)(*[int(x) for x in o])
+            assert helpers._emu.gmr_emu_set_lane_order(arr) == 0
+            q, it, err, tg, nfac = emu_retarget_batch(m, tt, pos, quat, ratio, bits=bits, nthreads=1)
+            ex = emu_retarget_batch_ex(m, tt, pos, quat, ratio, lengths=lengths, bits=bits)
+            results.append((q, it, err, tg, nfac) + tuple(ex))
+    finally:
+        helpers._emu.gmr_emu_set_lane_order((C.c_int * 32)(*range(32)))
+    assert results[0][4] > results[0][1].sum()                                           # the active-set path was exercised
+    for r in results[1:]:
+        for x, y in zip(results[0], r):
+            np.testing.assert_array_equal(np.asarray(x), np.asarray(y))
+    assert helpers._emu.gmr_emu_set_lane_order((C.c_int * 32)(*([0] * 32))) == -1         # not a permutation

@@ -9,8 +9,7 @@ for mix in "PROBE_ROBOT=unitree_g1 PROBE_SRC=smplx PROBE_C=4096 PROBE_T=300" \
            "PROBE_ROBOT=booster_t1 PROBE_SRC=bvh PROBE_C=8192 PROBE_T=300" \
            "PROBE_ROBOT=hightorque_hi PROBE_SRC=smplx PROBE_C=8192 PROBE_T=300" \
            "PROBE_ROBOT=kuavo_s45 PROBE_SRC=smplx PROBE_C=4096 PROBE_T=300"; do
-  for knobs in "GMR_NOTE=default" "GMR_PARTITION=0" "GMR_PARTITION=4 GMR_PARTITION_PCT=60" "GMR_PARTITION=6 GMR_PARTITION_PCT=60" \
-               "GMR_PARTITION=10" "GMR_SEGMENT=12" "GMR_SEGMENT=50"; do
+  for knobs in ${MIX_KNOBS:-"GMR_NOTE=default" "GMR_PARTITION=0" "GMR_PARTITION=6 GMR_PARTITION_PCT=60" "GMR_PARTITION=7 GMR_PARTITION_PCT=55" "GMR_PARTITION=10" "GMR_SEGMENT=50"}; do
     run $mix $knobs
   done
 done

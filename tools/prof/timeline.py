@@ -12,7 +12,7 @@ T = int(os.environ.get("PROBE_T", "300")); C = int(os.environ.get("PROBE_C", "40
 robot, cfg, _ = params.load_pack("smplx", "unitree_g1")
 table = compile_task_table(robot, cfg)
 gmr = GeneralMotionRetargeting("smplx", "unitree_g1", device=0)
-b = make_clips(robot, table, range(C), T=T, device="cuda")
+b = make_clips(robot, table, range(C), T=T, device="cuda", stress=os.environ.get("PROBE_STRESS", "0") == "1")
 dp, dq, dh = (torch.from_numpy(x).cuda() for x in (b.pos, b.quat, b.heights))
 lib = _native.load_library()
 lib.gmr_debug_trace.argtypes = [ctypes.c_void_p]; lib.gmr_debug_trace.restype = None
