@@ -50,6 +50,7 @@ static int gmr_emu_lane_order[32] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 1
 #define GMR_LANES for (int li_ = 0; li_ < 32; ++li_) { const int lane = gmr_emu_lane_order[li_]; LaneRegs<R>& L = lanes_[lane]; (void)L;
 #define GMR_END }
 #define GMR_UNROLL
+#define GMR_NOUNROLL
 #define GMR_SYNC()
 // end the lane loop, broadcast per-lane register(s) of lane `src` to every lane, open a new lane loop
 #define GMR_BCAST1(src, f0) } { const R bc0 = lanes_[src].f0; for (int li_ = 0; li_ < 32; ++li_) { const int lane = gmr_emu_lane_order[li_]; LaneRegs<R>& L = lanes_[lane]; (void)L;
@@ -68,6 +69,7 @@ static int gmr_emu_lane_order[32] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 1
 #define GMR_LANES { LaneRegs<R>& L = lanes_; const int lane = lane_; (void)L; (void)lane;
 #define GMR_END } __syncwarp();
 #define GMR_UNROLL _Pragma("unroll")
+#define GMR_NOUNROLL _Pragma("unroll 1")
 #define GMR_SYNC() __syncwarp()
 // warp shuffles: no shared-memory round trip and no extra __syncwarp for a one-lane -> all-lanes hand-over
 #define GMR_BCAST1(src, f0) const R bc0 = __shfl_sync(0xffffffffu, L.f0, src);
@@ -501,7 +503,7 @@ struct WarpSolver {
       }
       GMR_FK_SAVE
     GMR_END
-    GMR_UNROLL
+    GMR_NOUNROLL                                                      // one copy of the step in the instruction stream
     for (int k = 0; k < 4; k++) {
       if ((1 << k) <= dm.maxd) {                                        // a chain of maxd hinges + the root needs 2^K >= maxd + 1
         GMR_LANES
