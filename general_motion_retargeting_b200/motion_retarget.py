@@ -570,15 +570,17 @@ class GeneralMotionRetargeting:
             list(ex.map(one, zip(motions, paths)))
 
 
-def retarget_mixed(buckets, precision: str = "f64", return_info: bool = False, device=None):
+def retarget_mixed(buckets, precision: str = "f64", return_info: bool = False, device=None, out=None):
     """Mixed-robot batches (BASELINE.json configs[4]) in ONE call: `buckets` is a list of
     ``(retargeter, pos [C,T,nh,3], quat [C,T,nh,4], heights [C] or None)``, one entry per robot (group the clips with
     `sharding.bucket_by_robot`).  The arrays are torch CUDA tensors on one device, or torch CPU tensors in PINNED memory
     (``.pin_memory()``): those are used in place - the kernels read the keypoints over the host link and write qpos
     into pinned output tensors - and the call returns when the outputs are complete.  The device's SMs are divided
     among the buckets by work, so a bucket's slow clips overlap the other buckets' bulk instead of every bucket paying
-    its own tail.  Each clip is solved exactly as by `retargeter.retarget_batch`.  Returns the list of qpos tensors
-    ([C,T,nq] float32, on the inputs' side), with `return_info` also the per-frame iteration counts."""
+    its own tail.  Each clip is solved exactly as by `retargeter.retarget_batch`.  `out`: optional list of preallocated
+    float32 [C,T,nq] tensors, one per bucket, on the inputs' side (pinned for host buckets) - pinning gigabytes per call
+    costs more than the solve.  Returns the list of qpos tensors ([C,T,nq] float32, on the inputs' side), with
+    `return_info` also the per-frame iteration counts."""
     import torch
     if precision not in ("f32", "f64"):
         raise ValueError("precision must be 'f32' or 'f64'")
@@ -616,11 +618,19 @@ def retarget_mixed(buckets, precision: str = "f64", return_info: bool = False, d
                 d_ratio = torch.full((Cn,), g._ratio, dtype=torch.float32, device=dev)
             else:
                 d_ratio = (torch.as_tensor(heights).to(dev).to(torch.float64) / float(g._cfg.human_height_assumption)).to(torch.float32).contiguous()
-            if host:
+            if out is not None:
+                d_q = out[k]
+                ok = _is_torch(d_q) and d_q.dtype == torch.float32 and tuple(d_q.shape) == (Cn, T, nq) and d_q.is_contiguous() and \
+                    ((not d_q.is_cuda and d_q.is_pinned()) if host else (d_q.is_cuda and d_q.device == dev))
+                if not ok:
+                    raise ValueError(f"out[{k}] must be a contiguous float32 tensor of shape {(Cn, T, nq)} on the inputs' side")
+            elif host:
                 d_q = torch.empty((Cn, T, nq), dtype=torch.float32).pin_memory()
-                d_it = torch.zeros((Cn, T, 2), dtype=torch.int32).pin_memory() if return_info else None
             else:
                 d_q = torch.empty((Cn, T, nq), dtype=torch.float32, device=dev)
+            if host:
+                d_it = torch.zeros((Cn, T, 2), dtype=torch.int32).pin_memory() if return_info else None
+            else:
                 d_it = torch.zeros((Cn, T, 2), dtype=torch.int32, device=dev) if return_info else None
             h = g._handle(dev.index if dev.index is not None else torch.cuda.current_device())
             keep += [pos, quat, d_ratio, h]
