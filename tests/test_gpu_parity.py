@@ -339,40 +339,56 @@ def test_live_stream_matches_batch_and_carries_state(lib, torch_cuda):
 
 
 def test_two_phase_schedule_is_invisible(lib, torch_cuda):
-    """Batches of 1-4 GPU waves run as frame 0 -> classify -> frames 1.. with slow clips on their own SMs
-    (DESIGN.md §3), carried across the launches by a float64 state.  Pure scheduling: every output, including the
-    ragged lengths and the fused FK epilogue (running lowest height), must be bit-identical to a small batch that
-    takes the plain single-launch path."""
+    """Batches beyond 2 x SMs x 8 clips run as frame 0 -> classify -> scheduled launch (segments of 25 frames, slow / normal
+    rings, sparse and dense SMs: DESIGN.md section 3), carried across launches and segments by a float64 state record per clip.
+    Pure scheduling: every output, including ragged lengths, the fused FK epilogue (running lowest height), iteration counts,
+    errors and the per-clip status of clips that stop on bad input, must be bit-identical to small batches that take the plain
+    single-launch path.  A third of the clips are stress clips (unreachable targets: they stay in the slow class)."""
     torch = torch_cuda
-    from general_motion_retargeting_b200 import GeneralMotionRetargeting
+    from general_motion_retargeting_b200 import GeneralMotionRetargeting, _native
     m, tt, _ = problem("smplx", "unitree_g1")
-    Cn, T = 1400, 18                                           # > 2 * 148 SMs * 4 warps: two-phase
-    clips = make_clips(m, tt, range(800, 800 + Cn), T=T, device="cuda")
+    Cn, T = 2600, 56                                           # > 2 * 148 SMs * 8 warps: scheduled; 3 segments per clip
+    a = make_clips(m, tt, range(800, 800 + Cn), T=T, device="cuda")
+    b = make_clips(m, tt, range(800, 800 + Cn), T=T, device="cuda", stress=True)
+    pos, quat, heights = a.pos.copy(), a.quat.copy(), a.heights.copy()
+    pos[::3], quat[::3] = b.pos[::3], b.quat[::3]
+    pos[7, 30, 2, 1] = np.nan                                   # the reference would raise on these two clips
+    quat[11, 27, 5] = 0.0
     rng = np.random.default_rng(5)
     lengths = rng.integers(1, T + 1, Cn).astype(np.int32)
     lengths[:4] = [T, 1, 2, T]
+    lengths[[7, 11]] = T
     g = GeneralMotionRetargeting("smplx", "unitree_g1")
-    big = g.retarget_dataset(clips.pos, clips.quat, clips.heights, lengths=lengths, as_numpy=False)
-    sel = np.r_[0:40, 700:730, Cn - 30:Cn]                     # 100 clips: plain path
-    small = g.retarget_dataset(clips.pos[sel], clips.quat[sel], clips.heights[sel], lengths=lengths[sel], as_numpy=False)
+    big = g.retarget_dataset(pos, quat, heights, lengths=lengths, as_numpy=False, on_error="skip")
+    sel = np.r_[0:60, 1300:1345, Cn - 45:Cn]                   # 150 clips: plain path
+    small = g.retarget_dataset(pos[sel], quat[sel], heights[sel], lengths=lengths[sel], as_numpy=False, on_error="skip")
     idx = torch.from_numpy(sel).cuda()
-    for k in ("qpos", "root_pos", "root_rot", "dof_pos", "local_body_pos", "lowest_z"):
+    for k in ("qpos", "root_pos", "root_rot", "dof_pos", "local_body_pos", "lowest_z", "status"):
         assert torch.equal(big[k][idx], small[k]), k
+    st = big["status"].cpu().numpy()
+    assert st[7] == (_native.GMR_STATUS_BAD_INPUT | (30 << 8)) and st[11] == (_native.GMR_STATUS_BAD_INPUT | (27 << 8))
+    assert (np.delete(st, [7, 11]) & _native.GMR_STATUS_FATAL == 0).all()
     # and the iteration counts / errors through the batch entry
-    pos, quat, h = torch.from_numpy(clips.pos).cuda(), torch.from_numpy(clips.quat).cuda(), torch.from_numpy(clips.heights).cuda()
-    q, it, err = g.retarget_batch(pos, quat, h, return_info=True)
-    qs, its, errs = g.retarget_batch(pos[idx], quat[idx], h[idx], return_info=True)
-    assert torch.equal(q[idx], qs) and torch.equal(it[idx], its) and torch.equal(err[idx], errs)
+    dp, dq, dh = torch.from_numpy(pos).cuda(), torch.from_numpy(quat).cuda(), torch.from_numpy(heights).cuda()
+    q, it, err, status = g.retarget_batch(dp, dq, dh, return_info=True, on_error="status")
+    qs, its, errs, statuss = g.retarget_batch(dp[idx], dq[idx], dh[idx], return_info=True, on_error="status")
+    ok = torch.ones(len(sel), dtype=torch.bool, device="cuda"); ok[[7, 11]] = False      # stopped clips leave later frames unwritten
+    assert torch.equal(q[idx][ok], qs[ok]) and torch.equal(it[idx], its) and torch.equal(err[idx][ok], errs[ok]) and torch.equal(status[idx], statuss)
+    assert torch.equal(q[7, :30], qs[7, :30]) and torch.equal(q[11, :27], qs[11, :27])
+    assert float(it[::3].sum()) > 1.3 * float(it[1::3].sum())                               # the stress clips did take more steps
+    with pytest.raises(Exception) as ei:
+        g.retarget_batch(dp, dq, dh)
+    assert "RetargetFailure" in type(ei.value).__name__ and sorted(ei.value.clip_ids) == [7, 11]
 
 
 def test_host_entry_on_a_two_phase_batch_matches_device_path(lib, torch_cuda):
-    """gmr_retarget_batch_host on a batch large enough for the two-phase schedule (one chunk: copy in, two-phase
-    solve, copy out).  Same numbers as the device-resident entry (float32 buffers, float64 arithmetic), iteration
-    counts and errors included."""
+    """gmr_retarget_batch_host on a batch large enough for the scheduled launch, from pageable arrays (staged) and from
+    pinned arrays (used in place: the kernel reads and writes them over the host link).  Same numbers as the
+    device-resident entry (float32 buffers, float64 arithmetic), iteration counts and errors included."""
     torch = torch_cuda
     from general_motion_retargeting_b200 import GeneralMotionRetargeting
     m, tt, _ = problem("smplx", "unitree_g1")
-    Cn, T = 1300, 130
+    Cn, T = 2500, 60                                           # scheduled launch (> 2 x 148 x 8 clips), several segments per clip
     clips = make_clips(m, tt, range(300, 300 + Cn), T=T, device="cuda")
     g = GeneralMotionRetargeting("smplx", "unitree_g1")
     qh, ith, errh = g.retarget_batch(clips.pos, clips.quat, clips.heights, return_info=True)              # numpy -> host pipeline
@@ -387,6 +403,12 @@ def test_host_entry_on_a_two_phase_batch_matches_device_path(lib, torch_cuda):
     qd32 = g.retarget_batch(torch.from_numpy(clips.pos).cuda(), torch.from_numpy(clips.quat).cuda(),
                             torch.from_numpy(clips.heights).cuda(), precision="f32")
     np.testing.assert_array_equal(qh32, qd32.cpu().numpy())
+    # pinned arrays, in place (zero-copy in and out): bit-identical to the staged path
+    p_pos, p_quat = torch.from_numpy(clips.pos).pin_memory(), torch.from_numpy(clips.quat).pin_memory()
+    p_out = torch.full((Cn, T, m.nq), float("nan"), dtype=torch.float32).pin_memory()
+    qp = g.retarget_batch(p_pos.numpy(), p_quat.numpy(), clips.heights, out=p_out.numpy())
+    np.testing.assert_array_equal(qp, qh)
+    np.testing.assert_array_equal(p_out.numpy(), qh)
 
 
 def test_mixed_robot_launch_equals_per_robot_batches(lib, torch_cuda):
@@ -426,11 +448,11 @@ def test_mixed_pinned_host_buckets_and_multi_gpu_entry(lib, torch_cuda):
     torch = torch_cuda
     from general_motion_retargeting_b200 import GeneralMotionRetargeting, retarget_mixed
     from general_motion_retargeting_b200.dataset import plan_shards, retarget_clips_multi_gpu
-    specs = [("smplx", "unitree_g1", 700), ("smplx", "booster_t1", 640), ("smplx", "stanford_toddy", 33)]
+    specs = [("smplx", "unitree_g1", 1500), ("smplx", "booster_t1", 1200), ("smplx", "stanford_toddy", 33)]
     jobs, refs, host_buckets = [], [], []
     for k, (src, robot, n) in enumerate(specs):
         m, tt, _ = problem(src, robot)
-        clips = make_clips(m, tt, range(50 * k, 50 * k + n), T=18, src_human=src, device="cuda")
+        clips = make_clips(m, tt, range(50 * k, 50 * k + n), T=30, src_human=src, device="cuda")
         g = GeneralMotionRetargeting(src, robot, device=0)
         q, it, _ = g.retarget_batch(torch.from_numpy(clips.pos).cuda(), torch.from_numpy(clips.quat).cuda(),
                                     torch.from_numpy(clips.heights).cuda(), return_info=True)
