@@ -61,7 +61,7 @@ static int gmr_emu_lane_order[32] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 1
 #define GMR_DEPTH ((int)mc.hdepth[lane])
 #define GMR_DESC (mc.desc_mask[lane])
 #define GMR_SR (gmr_schur_r(lane))
-#define GMR_SC (gmr_schur_c(lane, dm.o_y))
+#define GMR_SC (gmr_schur_c<R>(lane))
 #define GMR_CTZ(x) __builtin_ctz(x)
 #else
 #define GMR_FN __device__ __forceinline__
@@ -87,12 +87,24 @@ static int gmr_emu_lane_order[32] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 1
 // ---- shared-memory layout of one warp's state (units: elements of R) -----------------------
 GMR_HD constexpr int gmr_pad4(int n) { return (n + 3) & ~3; }
 // Published factor row of hinge k (written when k is eliminated, read by its ancestors and by the
-// back substitution):  [ H'_k,base(6) | H'_k,anc(depth 1) .. H'_k,anc(depth d_k - 1) | junk up to o_y | y_k, 1/d_k, 0, 0 ]
+// back substitution):  [ y_k, 1/d_k (, 0, 0 in float32) | H'_k,base(6) | H'_k,anc(depth 1) .. H'_k,anc(depth d_k - 1) | junk up to o_y ]
+// (the header comes first so that every offset inside a row is a compile-time constant; Lrow(k) points at slot 0)
 // Slots are indexed by the DEPTH of the ancestor, not by its hinge number: every hinge on the chain root .. k
 // sees the same ancestor at the same slot, which is what lets lane i update row_i[s] -= a * row_k[s] with
 // statically indexed registers.
 GMR_HD constexpr int gmr_row_oy(int maxd) { return gmr_pad4(6 + (maxd > 0 ? maxd : 1)); }
-GMR_HD constexpr int gmr_row_stride(int maxd) { return gmr_row_oy(maxd) + 4; }
+// Record strides (elements of R).  Shared memory serves a 128-bit access of a quarter-warp in one wavefront only when the
+// eight 16-byte units fall into different bank groups: records that consecutive lanes touch are therefore laid out at a
+// stride that is ODD in 16-byte units (float64: 10-element poses = 5 units, 6-element spatial axes = 3, 30-element task
+// blocks = 15, factor rows 18 = 9; float32: 12-element poses = 3 units, 28-element task blocks = 7, factor rows 20 = 5).
+// ncu, round 2, balanced float64 batch: the shared-memory pipe was 73 % busy and 40 % of its wavefronts were bank
+// conflicts of the old power-of-two strides (profiles/r2_smem_wavefronts_before.txt).
+template <typename R> struct GmrLay;
+template <> struct GmrLay<double> { enum { PX = 10, SD = 6, TG = 10, MT = 30, ROWH = 2 }; };
+template <> struct GmrLay<float>  { enum { PX = 12, SD = 8, TG = 8,  MT = 28, ROWH = 4 }; };
+// the row stride is a compile-time constant (all GMR_NS slots, whatever the robot's deepest chain): row addresses are
+// k * constant + base, and the loop over all rows at the end of the factorisation unrolls with immediate offsets
+template <typename R> GMR_HD constexpr int gmr_row_stride(int) { return GMR_NS + GmrLay<R>::ROWH; }
 
 // fixed part
 enum {
@@ -114,28 +126,34 @@ enum { LP_F = 0, LP_DIAG = 6, LP_CI = 7, LP_X = 8 };
 // (<= 3 floats of slack in front, so that the TMA bulk copy of the aligned body lands 16-byte aligned) | quaternions nhum x 4 ]
 GMR_HD constexpr int gmr_in_quat(int nhum) { return gmr_pad4(3 * nhum + 4); }
 template <typename R> GMR_HD int gmr_in_elems(int nhum) { return gmr_pad4((int)(((gmr_in_quat(nhum) + 4 * nhum) * sizeof(float) + sizeof(R) - 1) / sizeof(R))); }
-// variable part: sd[8nh] tg[8nhum] in[staged floats] U, where the union U holds
-//   [ mt: task inertias, max(28 nt, 72) | xp: 4 nb | xq: 4 nb ]          while FK / task evaluation are live, and
-//   [ published factor rows, nh * stride ]                                  from the factorisation to the next FK.
+// variable part: U sd[SD nh] tg[TG nhum] in[staged floats], where the union U (first: its offset is a compile-time constant) holds
+//   [ mt: task blocks, MT nt | body poses, PX nb: (quat[4], pos[3], pad ..) ]   while FK / task evaluation are live, and
+//   [ published factor rows, nh * stride ]                                       from the factorisation to the next FK.
 // (body poses are dead once the composites are built; integrate() takes the root quaternion from GS_RQ.)
-GMR_HD constexpr int gmr_mt_elems(int nt) { return gmr_pad4(28 * nt > 72 ? 28 * nt : 72); }   // >= 2 (GMR_NH + 1) for the FK sin/cos table
+template <typename R> GMR_HD constexpr int gmr_mt_elems(int nt) { return gmr_pad4(GmrLay<R>::MT * nt); }
+template <typename R> GMR_HD constexpr int gmr_sd_elems(int nh) { return gmr_pad4(GmrLay<R>::SD * (nh > 0 ? nh : 1)); }
+template <typename R> GMR_HD int gmr_union_elems(int nb, int nh, int nt, int maxd) {
+  const int u = gmr_mt_elems<R>(nt) + gmr_pad4(GmrLay<R>::PX * nb);
+  const int lr = (nh > 0 ? nh : 1) * gmr_row_stride<R>(maxd);
+  return gmr_pad4(lr > u ? lr : u);
+}
 template <typename R> GMR_HD int gmr_warp_elems(int nb, int nh, int nhum, int nt, int maxd) {
-  int u = gmr_mt_elems(nt) + 4 * nb + 4 * nb;
-  const int lr = (nh > 0 ? nh : 1) * gmr_row_stride(maxd);
-  if (lr > u) u = lr;
-  return GS_VAR + 8 * (nh > 0 ? nh : 1) + 8 * nhum + gmr_in_elems<R>(nhum) + gmr_pad4(u);
+  return GS_VAR + gmr_union_elems<R>(nb, nh, nt, maxd) + gmr_sd_elems<R>(nh) + gmr_pad4(GmrLay<R>::TG * nhum) + gmr_in_elems<R>(nhum);
 }
 
 // fills the layout fields of `d` for precision R (host side, before launch)
 template <typename R> inline void gmr_dims_layout(GmrDims& d) {
-  int o = GS_VAR + 8 * (d.nh > 0 ? d.nh : 1);
-  d.o_tg = o; o += 8 * d.nhum;
-  d.o_in = o; o += gmr_in_elems<R>(d.nhum);
+  int o = GS_VAR;
   d.o_u = o;
-  d.o_xp = o + gmr_mt_elems(d.nt);
-  d.o_xq = d.o_xp + 4 * d.nb;
+  d.o_xq = o + gmr_mt_elems<R>(d.nt);       // poses are one record of PX elements per body: orientation at +0, position at +4
+  d.o_xp = d.o_xq + 4;
+  o += gmr_union_elems<R>(d.nb, d.nh, d.nt, d.maxd);
+  d.o_sd = o; o += gmr_sd_elems<R>(d.nh);
+  d.o_tg = o; o += gmr_pad4(GmrLay<R>::TG * d.nhum);
+  d.o_in = o; o += gmr_in_elems<R>(d.nhum);
   d.o_y = gmr_row_oy(d.maxd);
-  d.rs = gmr_row_stride(d.maxd);
+  d.rs = gmr_row_stride<R>(d.maxd);
+  d.rs_b = d.rs * (int)sizeof(R);
   d.warp_elems = gmr_warp_elems<R>(d.nb, d.nh, d.nhum, d.nt, d.maxd);
 }
 
@@ -161,6 +179,7 @@ template <typename R> struct LaneRegs {
   R dg;            // its diagonal
   R rhs, dinv;
   R sacc;          // lanes 0..26: one entry of the base block's Schur complement (accumulated during the elimination)
+  uint32_t piv;    // pivots of the depth being eliminated that this lane still has to absorb (its descendants)
 };
 
 // ---- tiny math helpers ----------------------------------------------------------------------
@@ -284,6 +303,36 @@ GMR_FN void g_st4(double* p, double a, double b, double c, double d) {
 #endif
 }
 
+// 2 consecutive elements (float64: one 128-bit access, 16-byte aligned; float32: one 64-bit access, 8-byte aligned)
+GMR_FN void g_ld2(const float* p, float* v) {
+#ifdef GMR_EMULATE
+  v[0] = p[0]; v[1] = p[1];
+#else
+  const float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y;
+#endif
+}
+GMR_FN void g_ld2(const double* p, double* v) {
+#ifdef GMR_EMULATE
+  v[0] = p[0]; v[1] = p[1];
+#else
+  const double2 t = *reinterpret_cast<const double2*>(p); v[0] = t.x; v[1] = t.y;
+#endif
+}
+GMR_FN void g_st2(float* p, float a, float b) {
+#ifdef GMR_EMULATE
+  p[0] = a; p[1] = b;
+#else
+  *reinterpret_cast<float2*>(p) = make_float2(a, b);
+#endif
+}
+GMR_FN void g_st2(double* p, double a, double b) {
+#ifdef GMR_EMULATE
+  p[0] = a; p[1] = b;
+#else
+  *reinterpret_cast<double2*>(p) = make_double2(a, b);
+#endif
+}
+
 template <typename R> GMR_FN void q_mul(const R* a, const R* b, R* o) {
   R w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
   R x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
@@ -349,7 +398,7 @@ template <typename R> GMR_FN void m3_skew(const R* v, R* S) {
 
 // lane e < 21 owns entry (r, c) of the packed upper triangle of the base block, lanes 21..26 its right-hand side
 GMR_HD constexpr int gmr_schur_r(int e) { return e < 21 ? (e >= 6) + (e >= 11) + (e >= 15) + (e >= 18) + (e >= 20) : (e < 27 ? e - 21 : 0); }
-GMR_HD constexpr int gmr_schur_c(int e, int o_y) { return e < 21 ? gmr_schur_r(e) + e - (gmr_schur_r(e) * (13 - gmr_schur_r(e))) / 2 : (e < 27 ? o_y : 0); }
+template <typename R> GMR_HD constexpr int gmr_schur_c(int e) { return e < 21 ? gmr_schur_r(e) + e - (gmr_schur_r(e) * (13 - gmr_schur_r(e))) / 2 : (e < 27 ? -(int)GmrLay<R>::ROWH : 0); }
 // index of (i,j) in the packed upper triangle of a symmetric 6x6 (21 entries)
 GMR_HD constexpr int gmr_sym6(int i, int j) { return i <= j ? (i * (13 - i)) / 2 + (j - i) : (j * (13 - j)) / 2 + (i - j); }
 
@@ -396,7 +445,7 @@ struct WarpSolver {
   int lane_;
   int dep_;                    // hinge depth of this lane (0: lane owns no hinge)
   uint32_t desc_;              // strict descendants of this lane's hinge
-  int sr_, sc_;                // this lane's entry of the base block (row slot, column slot)
+  int sr_, sc_;                // this lane's entry of the base block (row slot, column slot; the right-hand side is the row header)
 #endif
   int stat_refactor;           // factorisations done (uniform)
   uint32_t stat_flags;         // GMR_STATUS_* events of the current clip (uniform)
@@ -422,7 +471,7 @@ struct WarpSolver {
     lane_ = lane;
     dep_ = lane < d.nh ? (int)m.hdepth[lane] : 0;
     desc_ = lane < d.nh ? m.desc_mask[lane] : 0u;
-    sr_ = gmr_schur_r(lane); sc_ = gmr_schur_c(lane, d.o_y);
+    sr_ = gmr_schur_r(lane); sc_ = gmr_schur_c<R>(lane);
     sm_off = smem_byte_off;
 #else
     sm = smem;
@@ -441,17 +490,27 @@ struct WarpSolver {
   GMR_FN R* s_rq() const { return sm + GS_RQ; }
   GMR_FN R& lp(int slot, int lane) const { return *(sm + (GS_LP + slot * 32 + lane)); }
   GMR_FN R* s_q() const { return sm + GS_Q; }
-  GMR_FN R* s_sd() const { return sm + GS_VAR; }
+  GMR_FN R* s_sd() const { return sm + dm.o_sd; }
   GMR_FN R* s_tg() const { return sm + dm.o_tg; }
   GMR_FN float* s_in() const { return reinterpret_cast<float*>(sm + dm.o_in); }
   GMR_FN float* s_inq() const { return s_in() + gmr_in_quat(dm.nhum); }
   GMR_FN R* s_bar() const { return sm + GS_BAR; }
-  GMR_FN R* s_xp() const { return sm + dm.o_xp; }
+  enum { PX = GmrLay<R>::PX, SD = GmrLay<R>::SD, TG = GmrLay<R>::TG, MT = GmrLay<R>::MT };
+  GMR_FN R* s_xp() const { return sm + dm.o_xp; }   // body poses: record b at PX * b, position here, orientation at s_xq
   GMR_FN R* s_xq() const { return sm + dm.o_xq; }
-  GMR_FN R* s_U() const { return sm + dm.o_u; }
-  GMR_FN R* s_sc() const { return s_U(); }      // half-angle sin/cos, live only inside fk()
+  GMR_FN R* s_U() const { return sm + GS_VAR; }
   GMR_FN R* s_mt() const { return s_U(); }      // task inertias, dead once the rows are built
   GMR_FN R* s_L() const { return s_U(); }       // packed factor rows
+  enum { ROWH = GmrLay<R>::ROWH, ROWS = GMR_NS + GmrLay<R>::ROWH };
+  // slot 0 of the published row of hinge k; its header (y_k, 1/d_k) sits at [-ROWH], [-ROWH + 1]
+  GMR_FN R* Lrow(int k) const {
+#ifdef GMR_EMULATE
+    return sm + (GS_VAR + ROWH) + ROWS * k;
+#else
+    extern __shared__ __align__(128) unsigned char gmr_dyn_smem[];
+    return reinterpret_cast<R*>(gmr_dyn_smem + (sm_off + (uint32_t)k * (uint32_t)(ROWS * sizeof(R)))) + (GS_VAR + ROWH);   // one IMAD + an immediate
+#endif
+  }
 #ifndef GMR_EMULATE
   #undef sm
 #endif
@@ -491,8 +550,8 @@ struct WarpSolver {
         q[0] = c * A[0] + s * B[0]; q[1] = c * A[1] + s * B[1]; q[2] = c * A[2] + s * B[2]; q[3] = c * A[3] + s * B[3];
         p[0] = P[0]; p[1] = P[1]; p[2] = P[2];
         const int b = mc.hbody[lane];
-        g_st4(s_xq() + 4 * b, q[0], q[1], q[2], q[3]);
-        g_st4(s_xp() + 4 * b, p[0], p[1], p[2], R(0));
+        g_st4(s_xq() + PX * b, q[0], q[1], q[2], q[3]);
+        g_st4(s_xp() + PX * b, p[0], p[1], p[2], R(0));
       } else if (lane == dm.nh) {
         q[0] = s_q()[3]; q[1] = s_q()[4]; q[2] = s_q()[5]; q[3] = s_q()[6];
         q_normalize(q);
@@ -512,7 +571,7 @@ struct WarpSolver {
             const int pb = (int)((mc.fk_idx[lane] >> (8 * k)) & 0xffu);
             if (pb != 0xff) {
               R pq[4], pp[4];
-              g_ld4(s_xq() + 4 * pb, pq); g_ld4(s_xp() + 4 * pb, pp);
+              g_ld4(s_xq() + PX * pb, pq); g_ld4(s_xp() + PX * pb, pp);
               R off[3]; q_rot(pq, p, off);
               p[0] = pp[0] + off[0]; p[1] = pp[1] + off[1]; p[2] = pp[2] + off[2];
               R qn[4]; q_mul(pq, q, qn);
@@ -527,8 +586,8 @@ struct WarpSolver {
           GMR_FK_LOAD
           if (lane < dm.nh && ((mc.fk_idx[lane] >> (8 * k)) & 0xffu) != 0xff) {
             const int b = mc.hbody[lane];
-            g_st4(s_xq() + 4 * b, q[0], q[1], q[2], q[3]);
-            g_st4(s_xp() + 4 * b, p[0], p[1], p[2], R(0));
+            g_st4(s_xq() + PX * b, q[0], q[1], q[2], q[3]);
+            g_st4(s_xp() + PX * b, p[0], p[1], p[2], R(0));
           }
         GMR_END
       }
@@ -537,21 +596,21 @@ struct WarpSolver {
       GMR_FK_LOAD
       if (lane < dm.nh) {
         R w[3]; q_rot(q, mc.axis + 3 * lane, w);
-        R* o = s_sd() + 8 * lane;
+        R* o = s_sd() + SD * lane;
         // linear velocity of the reference point (root origin) under unit joint rate: w x (0 - d) = d x w
         g_st4(o, p[1] * w[2] - p[2] * w[1], p[2] * w[0] - p[0] * w[2], p[0] * w[1] - p[1] * w[0], w[0]);
-        g_st4(o + 4, w[1], w[2], R(0), R(0));
+        g_st2(o + 4, w[1], w[2]);
       }
       for (int e = dm.nh + lane; e < dm.nb - 1; e += 32) {               // fixed bodies: constant pose in a moving body's frame
         const uint32_t ix = mc.fk_idx[e];
         const int b = ix & 0xffu, ab = (ix >> 8) & 0xffu;
         R aq[4], ap[4], C[4], Cp[4];
-        g_ld4(s_xq() + 4 * ab, aq); g_ld4(s_xp() + 4 * ab, ap);
+        g_ld4(s_xq() + PX * ab, aq); g_ld4(s_xp() + PX * ab, ap);
         g_ld4(mc.fk_A + 4 * e, C); g_ld4(mc.fk_pos + 4 * e, Cp);
         R off[3]; q_rot(aq, Cp, off);
         R qf[4]; q_mul(aq, C, qf);
-        g_st4(s_xp() + 4 * b, ap[0] + off[0], ap[1] + off[1], ap[2] + off[2], R(0));
-        g_st4(s_xq() + 4 * b, qf[0], qf[1], qf[2], qf[3]);
+        g_st4(s_xp() + PX * b, ap[0] + off[0], ap[1] + off[1], ap[2] + off[2], R(0));
+        g_st4(s_xq() + PX * b, qf[0], qf[1], qf[2], qf[3]);
       }
     GMR_END
 #undef GMR_FK_LOAD
@@ -591,9 +650,9 @@ struct WarpSolver {
         n = R(1) / g_sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2] + u[3] * u[3]);
         u[0] *= n; u[1] *= n; u[2] *= n; u[3] *= n;
         R g[3]; q_rot(u, mc.hpoff + 3 * lane, g);
-        R* o = s_tg() + 8 * lane;
-        o[0] = p[0] + g[0]; o[1] = p[1] + g[1]; o[2] = p[2] + g[2]; o[3] = R(0);
-        o[4] = u[0]; o[5] = u[1]; o[6] = u[2]; o[7] = u[3];
+        R* o = s_tg() + TG * lane;
+        g_st4(o, p[0] + g[0], p[1] + g[1], p[2] + g[2], R(0));
+        g_st4(o + 4, u[0], u[1], u[2], u[3]);
       }
 #ifdef GMR_EMULATE
       if (!fin) ok = false;
@@ -603,10 +662,10 @@ struct WarpSolver {
     GMR_END
     if (to_ground) {      // offset_human_data_to_ground, motion_retarget.py:252-270
       R lowest = R(INFINITY);
-      for (int h = 0; h < dm.nhum; h++) if ((dm.foot_mask >> h) & 1u) { R z = s_tg()[8 * h + 2]; if (z < lowest) lowest = z; }
+      for (int h = 0; h < dm.nhum; h++) if ((dm.foot_mask >> h) & 1u) { R z = s_tg()[TG * h + 2]; if (z < lowest) lowest = z; }
       GMR_SYNC();
       GMR_LANES
-        if (lane < dm.nhum) s_tg()[8 * lane + 2] = s_tg()[8 * lane + 2] - lowest + R(0.1);
+        if (lane < dm.nhum) s_tg()[TG * lane + 2] = s_tg()[TG * lane + 2] - lowest + R(0.1);
       GMR_END
     }
     return ok;
@@ -627,9 +686,9 @@ struct WarpSolver {
     GMR_LANES
       if (lane < dm.nt) {
         const int b = mc.tbody[lane], h = mc.thuman[lane];
-        const R* tg = s_tg() + 8 * h;
-        R qb[4]; g_ld4(s_xq() + 4 * b, qb);
-        R d[4]; g_ld4(s_xp() + 4 * b, d);
+        const R* tg = s_tg() + TG * h;
+        R qb[4]; g_ld4(s_xq() + PX * b, qb);
+        R d[4]; g_ld4(s_xp() + PX * b, d);
         R qi[4] = {qb[0], -qb[1], -qb[2], -qb[3]};
         R qt[4]; g_ld4(tg + 4, qt);
         R qe[4]; q_mul(qi, qt, qe);
@@ -655,7 +714,7 @@ struct WarpSolver {
         R rho[3] = {tb[0] - R(0.5) * c1[0] + cV * c2[0], tb[1] - R(0.5) * c1[1] + cV * c2[1], tb[2] - R(0.5) * c1[2] + cV * c2[2]};
         s_red()[lane] = rho[0] * rho[0] + rho[1] * rho[1] + rho[2] * rho[2] + th2;
         // hand-over to task_build(): parked in the task's own (still unused) M_t block rather than in registers
-        R* o = s_mt() + 28 * lane;
+        R* o = s_mt() + MT * lane;
         g_st4(o, om[0], om[1], om[2], th2); g_st4(o + 4, rho[0], rho[1], rho[2], nsq);
         g_st4(o + 8, d[0], d[1], d[2], qe[0]); g_st4(o + 12, qb[0], qb[1], qb[2], qb[3]);
         o[16] = cV;
@@ -668,7 +727,7 @@ struct WarpSolver {
     GMR_LANES
       if (lane < dm.nt) {
         R om[4], rho[4], d[4], qb[4], P[9], K[9];
-        const R* in = s_mt() + 28 * lane;
+        const R* in = s_mt() + MT * lane;
         g_ld4(in, om); g_ld4(in + 4, rho); g_ld4(in + 8, d); g_ld4(in + 12, qb);
         const R th2 = om[3], nsq = rho[3], cw = d[3], cV = in[16];
         {
@@ -723,11 +782,12 @@ struct WarpSolver {
           for (int i = 0; i < 9; i++) K[i] = -T2[i] - PS[i];
         }
         const R r2 = rho[0] * rho[0] + rho[1] * rho[1] + rho[2] * rho[2];
-        R* o = s_mt() + 28 * lane;
+        R* o = s_mt() + MT * lane;
         const bool on = (stage_mask >> lane) & 1u;
         const R* wtab = stage == 0 ? mc.w1 : mc.w2;
         const R wp = on ? wtab[2 * lane] : R(0), wr = on ? wtab[2 * lane + 1] : R(0);
         const R wp2 = wp * wp, wr2 = wr * wr;
+        R blk[28];                                            // assembled in registers (static indices), stored as 128-bit units
         {
           R PtP[9], PtK[9], KtK[9];
           m3_mul_at(P, P, PtP); m3_mul_at(P, K, PtK); m3_mul_at(K, K, KtK);
@@ -735,8 +795,8 @@ struct WarpSolver {
           for (int i = 0; i < 3; i++) {
             GMR_UNROLL
             for (int j = 0; j < 3; j++) {
-              if (j >= i) { o[gmr_sym6(i, j)] = wp2 * PtP[3 * i + j]; o[gmr_sym6(3 + i, 3 + j)] = wp2 * KtK[3 * i + j] + wr2 * PtP[3 * i + j]; }
-              o[gmr_sym6(i, 3 + j)] = wp2 * PtK[3 * i + j];
+              if (j >= i) { blk[gmr_sym6(i, j)] = wp2 * PtP[3 * i + j]; blk[gmr_sym6(3 + i, 3 + j)] = wp2 * KtK[3 * i + j] + wr2 * PtP[3 * i + j]; }
+              blk[gmr_sym6(i, 3 + j)] = wp2 * PtK[3 * i + j];
             }
           }
         }
@@ -745,10 +805,12 @@ struct WarpSolver {
           const R ptr = P[i] * rho[0] + P[3 + i] * rho[1] + P[6 + i] * rho[2];
           const R ktr = K[i] * rho[0] + K[3 + i] * rho[1] + K[6 + i] * rho[2];
           const R pto = P[i] * om[0] + P[3 + i] * om[1] + P[6 + i] * om[2];
-          o[21 + i] = -(wp2 * ptr);
-          o[24 + i] = -(wp2 * ktr + wr2 * pto);
+          blk[21 + i] = -(wp2 * ptr);
+          blk[24 + i] = -(wp2 * ktr + wr2 * pto);
         }
-        o[27] = ks.lm * (wp2 * r2 + wr2 * th2);
+        blk[27] = ks.lm * (wp2 * r2 + wr2 * th2);
+        GMR_UNROLL
+        for (int c = 0; c < 7; c++) g_st4(o + 4 * c, blk[4 * c], blk[4 * c + 1], blk[4 * c + 2], blk[4 * c + 3]);
       }
     GMR_END
   }
@@ -783,10 +845,19 @@ struct WarpSolver {
           const int q = lane / 7, c = lane - 7 * q;
           const uint32_t tp = mc.tround[4 * r + q];
           if (tp != 0xffffu) {                               // unused slot of the round
-            R* dst = s_mt() + 28 * (tp >> 8) + 4 * c;
-            R a[4], b[4];
-            g_ld4(s_mt() + 28 * (tp & 0xffu) + 4 * c, a); g_ld4(dst, b);
-            g_st4(dst, a[0] + b[0], a[1] + b[1], a[2] + b[2], a[3] + b[3]);
+            R* dst = s_mt() + MT * (tp >> 8);
+            const R* src = s_mt() + MT * (tp & 0xffu);
+            if constexpr (sizeof(R) == 8) {
+              // a lane's four elements as two 16-byte units that are 7 units apart: the seven lanes of a pair then
+              // touch consecutive units in each access (4 c .. 4 c + 3 would put lanes c and c + 4 on the same banks)
+              R a[2], b[2], a2[2], b2[2];
+              g_ld2(src + 2 * c, a); g_ld2(dst + 2 * c, b); g_ld2(src + 14 + 2 * c, a2); g_ld2(dst + 14 + 2 * c, b2);
+              g_st2(dst + 2 * c, a[0] + b[0], a[1] + b[1]); g_st2(dst + 14 + 2 * c, a2[0] + b2[0], a2[1] + b2[1]);
+            } else {
+              R a[4], b[4];
+              g_ld4(src + 4 * c, a); g_ld4(dst + 4 * c, b);
+              g_st4(dst + 4 * c, a[0] + b[0], a[1] + b[1], a[2] + b[2], a[3] + b[3]);
+            }
           }
         }
       GMR_END
@@ -795,7 +866,7 @@ struct WarpSolver {
       if (lane < 28) {
         R s = R(0);
         uint32_t rm = mc.troot_mask;
-        while (rm) { const int t = GMR_CTZ(rm); rm &= rm - 1u; s += s_mt()[28 * t + lane]; }
+        while (rm) { const int t = GMR_CTZ(rm); rm &= rm - 1u; s += s_mt()[MT * t + lane]; }
         s_root()[lane] = s;
       }
     GMR_END
@@ -806,7 +877,7 @@ struct WarpSolver {
         // most hinges of a humanoid); the trip count is the longest such list of the robot
         uint32_t tm = mc.top_mask[lane];
         if (tm) {                                            // the first (usually only) one is a plain load
-          const R* m = s_mt() + 28 * GMR_CTZ(tm);
+          const R* m = s_mt() + MT * GMR_CTZ(tm);
           tm &= tm - 1u;
           GMR_UNROLL
           for (int c = 0; c < 7; c++) g_ld4(m + 4 * c, acc + 4 * c);
@@ -818,7 +889,7 @@ struct WarpSolver {
           if (tm) {
             const int t = GMR_CTZ(tm);
             tm &= tm - 1u;
-            const R* m = s_mt() + 28 * t;
+            const R* m = s_mt() + MT * t;
             GMR_UNROLL
             for (int c = 0; c < 7; c++) {
               R v[4]; g_ld4(m + 4 * c, v);
@@ -826,7 +897,7 @@ struct WarpSolver {
             }
           }
         }
-        R sv[8]; g_ld4(s_sd() + 8 * lane, sv); g_ld4(s_sd() + 8 * lane + 4, sv + 4);
+        R sv[6]; g_ld4(s_sd() + SD * lane, sv); g_ld2(s_sd() + SD * lane + 4, sv + 4);
         R dg = R(0), ci = R(0);
         GMR_UNROLL
         for (int i = 0; i < 6; i++) {
@@ -858,18 +929,31 @@ struct WarpSolver {
         R f[6];
         GMR_UNROLL
         for (int g = 0; g < 6; g++) { f[g] = act ? lp(LP_F + g, lane) : R(0); L.row[g] = f[g]; }
+        // Branch-free across the lanes: a lane without an ancestor at depth d reads its own axis (the table holds its own
+        // index there) and discards the product.  The depths then sit in two straight-line blocks - 1..6, and 7..9 for
+        // robots with chains deeper than 7 hinges - whose load -> FMA chains overlap instead of running one after the
+        // other behind branches (a warp issues in order; measured on a lone slow clip: 5.7 % of its time was here).
+        static_assert(GMR_MAXD == 10, "the depth split below assumes ten slots");
         GMR_UNROLL
-        for (int d = 1; d <= GMR_MAXD; d++) {
-          R v = R(0);
-          if (d < dm.maxd) {                                   // no hinge has a strict ancestor at depth maxd
-            if (d < dep) {
-              const int j = mc.anc_of[lane * GMR_MAXD + d - 1];
-              R s[8]; g_ld4(s_sd() + 8 * j, s); g_ld4(s_sd() + 8 * j + 4, s + 4);
-              v = f[0] * s[0] + f[1] * s[1] + f[2] * s[2] + f[3] * s[3] + f[4] * s[4] + f[5] * s[5];
-            }
-          }
-          L.row[5 + d] = v;
+        for (int d = 1; d <= 6; d++) {
+          const int j = mc.anc_of[lane * GMR_MAXD + d - 1];
+          R s[6]; g_ld4(s_sd() + SD * j, s); g_ld2(s_sd() + SD * j + 4, s + 4);
+          const R t = f[0] * s[0] + f[1] * s[1] + f[2] * s[2] + f[3] * s[3] + f[4] * s[4] + f[5] * s[5];
+          L.row[5 + d] = d < dep ? t : R(0);
         }
+        if (dm.maxd > 7) {                                       // uniform
+          GMR_UNROLL
+          for (int d = 7; d < GMR_MAXD; d++) {
+            const int j = mc.anc_of[lane * GMR_MAXD + d - 1];
+            R s[6]; g_ld4(s_sd() + SD * j, s); g_ld2(s_sd() + SD * j + 4, s + 4);
+            const R t = f[0] * s[0] + f[1] * s[1] + f[2] * s[2] + f[3] * s[3] + f[4] * s[4] + f[5] * s[5];
+            L.row[5 + d] = d < dep ? t : R(0);
+          }
+        } else {
+          GMR_UNROLL
+          for (int d = 7; d < GMR_MAXD; d++) L.row[5 + d] = R(0);
+        }
+        L.row[5 + GMR_MAXD] = R(0);                              // no hinge has a strict ancestor at depth GMR_MAXD
         L.dg = act ? lp(LP_DIAG, lane) : R(1);
         L.rhs = act ? -lp(LP_CI, lane) : R(0);
         L.dinv = R(1);
@@ -884,44 +968,56 @@ struct WarpSolver {
       if (c < nchunk) g_st4(o + 4 * c, L.row[4 * c] * sc, L.row[4 * c + 1] * sc, L.row[4 * c + 2] * sc, L.row[4 * c + 3] * sc);
   }
 
+  // sum of term(p) over the set bits p of m, four terms at a time: their loads are issued together (a warp issues in order: a
+  // plain loop pays one shared-memory round trip per bit)
+  template <typename F> GMR_FN R sum_over_bits(uint32_t m, F term) const {
+    R acc = R(0);
+    while (m) {
+      const int p0 = GMR_CTZ(m); m &= m - 1u;
+      const bool h1 = m != 0u; const int p1 = h1 ? GMR_CTZ(m) : p0; m &= m - 1u;
+      const bool h2 = m != 0u; const int p2 = h2 ? GMR_CTZ(m) : p0; m &= m - 1u;
+      const bool h3 = m != 0u; const int p3 = h3 ? GMR_CTZ(m) : p0; m &= m - 1u;
+      const R t0 = term(p0), t1 = term(p1), t2 = term(p2), t3 = term(p3);
+      acc += t0; acc += h1 ? t1 : R(0); acc += h2 ? t2 : R(0); acc += h3 ? t3 : R(0);
+    }
+    return acc;
+  }
+
   // Working set: a pinned hinge p keeps x_p = bound.  Its row becomes the identity with rhs = bound, its
   // column moves to the right-hand side of every row coupled to it (ancestors, descendants, base).
   GMR_FN void apply_pins(uint32_t pinned) {
     const int nchunk_all = dm.o_y >> 2;
     GMR_LANES
-      if (lane < dm.nh && ((pinned >> lane) & 1u))
-        publish_row(s_L() + dm.rs * lane, L, s_bnd()[lane], nchunk_all);      // (row of H) * bound
+      if (lane < dm.nh && ((pinned >> lane) & 1u)) {
+        R* o = Lrow(lane);
+        publish_row(o, L, s_bnd()[lane], nchunk_all);               // (row of H) * bound
+        g_st2(o - ROWH, R(0), R(0));                                  // header: "1 / d = 0" - no contribution to the base block
+      }
     GMR_END
+    // straight-line per lane (selects instead of branches: the nine depths' table look-ups, bound loads and FMAs overlap)
     GMR_LANES
-      if (lane < dm.nh) {
-        const int dep = GMR_DEPTH;
-        if ((pinned >> lane) & 1u) {
-          GMR_UNROLL
-          for (int s = 0; s < GMR_NS; s++) L.row[s] = R(0);
-          L.dg = R(1);
-          L.rhs = s_bnd()[lane];
-        } else {
-          R r = L.rhs;
-          if (mc.anc_mask[lane] & pinned) {                     // pinned ancestors: my own slots
-            GMR_UNROLL
-            for (int d = 1; d < GMR_MAXD; d++) {
-              if (d < dep) {
-                const int j = mc.anc_of[lane * GMR_MAXD + d - 1];
-                if ((pinned >> j) & 1u) { r -= L.row[5 + d] * s_bnd()[j]; L.row[5 + d] = R(0); }
-              }
-            }
-          }
-          uint32_t ds = mc.desc_mask[lane] & pinned;            // pinned descendants: their published rows
-          while (ds) { const int p = GMR_CTZ(ds); ds &= ds - 1u; r -= s_L()[dm.rs * p + 5 + dep]; }
-          L.rhs = r;
+      {
+        const int dep = GMR_DEPTH;                                // 0 for a lane without a hinge: nothing below applies to it
+        const bool mine = (pinned >> lane) & 1u;
+        R r = L.rhs;
+        GMR_UNROLL
+        for (int d = 1; d < GMR_MAXD; d++) {                      // pinned ancestors: my own slots
+          const int j = mc.anc_of[lane * GMR_MAXD + d - 1];
+          const bool pj = d < dep && ((pinned >> j) & 1u);
+          const R t = r - L.row[5 + d] * s_bnd()[j];              // s_bnd of an unpinned hinge is stale: computed, not selected
+          r = pj ? t : r;
+          L.row[5 + d] = (pj || mine) ? R(0) : L.row[5 + d];
         }
+        // pinned descendants: their published rows
+        r -= sum_over_bits(GMR_DESC & pinned, [&](int p) { return Lrow(p)[5 + dep]; });
+        GMR_UNROLL
+        for (int g = 0; g < 6; g++) L.row[g] = mine ? R(0) : L.row[g];
+        L.row[5 + GMR_MAXD] = mine ? R(0) : L.row[5 + GMR_MAXD];
+        L.dg = mine ? R(1) : L.dg;
+        L.rhs = mine ? s_bnd()[lane] : r;
       }
-      if (lane < 6) {                                           // base right-hand side correction -> s_xs[0..5]
-        R r = R(0);
-        uint32_t ps = pinned;
-        while (ps) { const int p = GMR_CTZ(ps); ps &= ps - 1u; r += s_L()[dm.rs * p + lane]; }
-        s_xs()[lane] = r;
-      }
+      if (lane < 6)                                             // base right-hand side correction -> s_xs[0..5]
+        s_xs()[lane] = sum_over_bits(pinned, [&](int p) { return Lrow(p)[lane]; });
     GMR_END
   }
 
@@ -933,37 +1029,55 @@ struct WarpSolver {
       if (GMR_DEPTH == lv && !((pinned >> lane) & 1u)) {
         const R di = g_rcp_pos(L.dg);
         L.dinv = di;
-        R* o = s_L() + dm.rs * lane;
+        R* o = Lrow(lane);
         publish_row(o, L, R(1), NCH);
-        g_st4(o + dm.o_y, L.rhs, di, R(0), R(0));
+        if constexpr (sizeof(R) == 8) g_st2(o - ROWH, L.rhs, di); else g_st4(o - ROWH, L.rhs, di, R(0), R(0));
       }
     GMR_END
     // float32: two pivots per pass, branch-free — every lane loads both published rows (broadcast reads) and absorbs
     // them with a multiplier that is zero unless the lane is an ancestor of that pivot; a lone pivot is paired with
     // itself at zero weight.  No divergent branch, the loads of the second pivot overlap the FMAs of the first
-    // (lone warp -8 %).  float64 keeps one pivot per pass behind a branch: its FMAs are the scarce resource (the FP64
+    // (lone warp -8 %).  float64 keeps the update behind a branch: its FMAs are the scarce resource (the FP64
     // pipe is half rate), and the paired form issues ~10 % more of them.
     uint32_t rem = mc.lvl_mask[lv] & ~pinned;
     if constexpr (sizeof(R) == 8) {
-      while (rem) {
-        const int k = GMR_CTZ(rem);
-        rem &= rem - 1u;
+      // float64: every lane absorbs ITS OWN next pivot in a pass - pivots of one depth in different branches (left /
+      // right leg, left / right arm) have different ancestors, so their row updates run side by side: for G1 16
+      // passes instead of 29 (a lane still sees its pivots in ascending order: the results are unchanged bit for bit).
+      // The base block's rank-1 updates of this depth follow in factor_solve (base_block_depth).
+      bool more = false;
+      GMR_LANES
+        L.piv = GMR_DESC & rem;
+#ifdef GMR_EMULATE
+        if (L.piv) more = true;
+#else
+        more = __any_sync(0xffffffffu, L.piv != 0u);
+#endif
+      GMR_END_NOSYNC
+      while (more) {
+#ifdef GMR_EMULATE
+        more = false;
+#endif
         GMR_LANES
-          const R* pk = s_L() + dm.rs * k;
-          const R yk = pk[dm.o_y], dk = pk[dm.o_y + 1];
-          if ((GMR_DESC >> k) & 1u) {
+          if (L.piv) {
+            const R* pk = Lrow(GMR_CTZ(L.piv));
+            L.piv &= L.piv - 1u;
+            R yd[2]; g_ld2(pk - ROWH, yd);                         // y_k, 1 / d_k
             const R hki = pk[5 + GMR_DEPTH];
-            const R a = hki * dk;
+            const R a = hki * yd[1];
             GMR_UNROLL
             for (int c = 0; c < NCH; c++) {
               R v[4]; g_ld4(pk + 4 * c, v);
               L.row[4 * c] -= a * v[0]; L.row[4 * c + 1] -= a * v[1]; L.row[4 * c + 2] -= a * v[2]; L.row[4 * c + 3] -= a * v[3];
             }
             L.dg -= a * hki;
-            L.rhs -= a * yk;
+            L.rhs -= a * yd[0];
           }
-          // base block: S = A_bb - sum_k (1/d_k) h_k h_k^T,  b = b_b - sum_k (1/d_k) h_k y_k,  h_k = base slots of row k
-          if (lane < 27) L.sacc += pk[GMR_SR] * dk * pk[GMR_SC];
+#ifdef GMR_EMULATE
+          if (L.piv) more = true;
+#else
+          more = __any_sync(0xffffffffu, L.piv != 0u);
+#endif
         GMR_END_NOSYNC
       }
     } else {
@@ -974,9 +1088,9 @@ struct WarpSolver {
       const int k1 = two ? GMR_CTZ(rem) : k0;
       rem &= rem - 1u;                                               // (0 & anything) stays 0
       GMR_LANES
-        const R* p0 = s_L() + dm.rs * k0;
-        const R* p1 = s_L() + dm.rs * k1;
-        const R y0 = p0[dm.o_y], d0 = p0[dm.o_y + 1], y1 = p1[dm.o_y], d1 = two ? p1[dm.o_y + 1] : R(0);
+        const R* p0 = Lrow(k0);
+        const R* p1 = Lrow(k1);
+        const R y0 = p0[-ROWH], d0 = p0[-ROWH + 1], y1 = p1[-ROWH], d1 = two ? p1[-ROWH + 1] : R(0);
         const R h0 = p0[5 + GMR_DEPTH], h1 = p1[5 + GMR_DEPTH];
         const R a0 = ((GMR_DESC >> k0) & 1u) ? h0 * d0 : R(0), a1 = ((GMR_DESC >> k1) & 1u) ? h1 * d1 : R(0);
         GMR_UNROLL
@@ -1009,7 +1123,7 @@ struct WarpSolver {
   GMR_FN void factor_solve(uint32_t pinned) {
     const bool pinned_any = pinned != 0;
     // per-lane constants of this factorisation: my descendants, my entry (r, cc) of the base block
-    // (lanes 0..20: packed upper triangle; lanes 21..26: the right-hand side, "column" o_y)
+    // (lanes 0..20: packed upper triangle; lanes 21..26: the right-hand side, the row header's y)
     GMR_LANES
       L.sacc = R(0);
     GMR_END_NOSYNC
@@ -1021,6 +1135,28 @@ struct WarpSolver {
         case 3: eliminate_depth<3>(lv, pinned); break;
         default: eliminate_depth<GMR_NS / 4>(lv, pinned); break;
       }
+    }
+    if constexpr (sizeof(R) == 8) {
+      // base block: S = A_bb - sum_k (1/d_k) h_k h_k^T,  b = b_b - sum_k (1/d_k) h_k y_k,  h_k = base slots of the
+      // published row k.  Every row is still in place after the last depth (pinned rows carry 1/d = 0), so one loop over
+      // all rows does it: constant stride, immediate offsets, the loads of several rows in flight at once; two partial
+      // sums halve the dependent chain.  Lanes >= 27 own "entry (0, 0)" and are never read.
+      GMR_LANES
+        const R* pr = Lrow(0) + GMR_SR;
+        const R* pc = Lrow(0) + GMR_SC;
+        const R* pd = Lrow(0) - ROWH + 1;
+        R s0 = R(0), s1 = R(0);
+        int k = 0;
+        GMR_NOUNROLL
+        for (; k + 4 <= dm.nh; k += 4) {
+          const R a0 = pr[0] * pd[0], a1 = pr[ROWS] * pd[ROWS], a2 = pr[2 * ROWS] * pd[2 * ROWS], a3 = pr[3 * ROWS] * pd[3 * ROWS];
+          s0 += a0 * pc[0]; s1 += a1 * pc[ROWS]; s0 += a2 * pc[2 * ROWS]; s1 += a3 * pc[3 * ROWS];
+          pr += 4 * ROWS; pc += 4 * ROWS; pd += 4 * ROWS;
+        }
+        GMR_NOUNROLL
+        for (; k < dm.nh; k++) { s0 += (pr[0] * pd[0]) * pc[0]; pr += ROWS; pc += ROWS; pd += ROWS; }
+        L.sacc = s0 + s1;
+      GMR_END_NOSYNC
     }
     GMR_LANES
       if (lane < 27) {
@@ -1209,23 +1345,21 @@ struct WarpSolver {
       // (its row) * x_lane, a pinned lane adds its own slots times the ancestors' x and collects its
       // column from the published rows of its descendants.
       GMR_LANES
-        if (lane < dm.nh) publish_row(s_L() + dm.rs * lane, L, lp(LP_X, lane), dm.o_y >> 2);
+        if (lane < dm.nh) publish_row(Lrow(lane), L, lp(LP_X, lane), dm.o_y >> 2);
       GMR_END
       GMR_LANES
-        if (lane < dm.nh) {
-          R lam = INF;
-          if ((pinned >> lane) & 1u) {
-            const int dep = GMR_DEPTH;
-            R g = lp(LP_CI, lane) + L.dg * lp(LP_X, lane);
-            GMR_UNROLL
-            for (int f = 0; f < 6; f++) g += L.row[f] * s_xs()[f];
-            GMR_UNROLL
-            for (int d = 1; d < GMR_MAXD; d++) if (d < dep) g += L.row[5 + d] * s_xs()[6 + mc.anc_of[lane * GMR_MAXD + d - 1]];
-            uint32_t ds = mc.desc_mask[lane];
-            while (ds) { const int k = GMR_CTZ(ds); ds &= ds - 1u; g += s_L()[dm.rs * k + 5 + dep]; }
-            lam = ((pin_lo >> lane) & 1u) ? g : -g;
-          }
-          s_red()[lane] = lam;
+        {
+          // straight-line (a lane that is not pinned computes a value it discards): rows hold zeros in the slots a hinge
+          // does not have, and the table names the hinge itself there
+          const bool mine = (pinned >> lane) & 1u;
+          const int dep = GMR_DEPTH;
+          R g = lp(LP_CI, lane) + L.dg * lp(LP_X, lane);
+          GMR_UNROLL
+          for (int f = 0; f < 6; f++) g += L.row[f] * s_xs()[f];
+          GMR_UNROLL
+          for (int d = 1; d < GMR_MAXD; d++) g += L.row[5 + d] * s_xs()[6 + mc.anc_of[lane * GMR_MAXD + d - 1]];
+          g += sum_over_bits(mine ? GMR_DESC : 0u, [&](int k) { return Lrow(k)[5 + dep]; });
+          if (lane < dm.nh) s_red()[lane] = mine ? (((pin_lo >> lane) & 1u) ? g : -g) : INF;
         }
       GMR_END
       // release: the first two checks of a solve drop EVERY bound with a multiplier of the wrong sign (a
@@ -1550,7 +1684,7 @@ struct WarpSolver {
           }
           if (io.tg && lane < dm.nhum) {
             IO* o = io.tg + (f * dm.nhum + lane) * 7;
-            const R* g = s_tg() + 8 * lane;
+            const R* g = s_tg() + TG * lane;
             o[0] = IO(g[0]); o[1] = IO(g[1]); o[2] = IO(g[2]); o[3] = IO(g[4]); o[4] = IO(g[5]); o[5] = IO(g[6]); o[6] = IO(g[7]);
           }
         GMR_END
@@ -1559,7 +1693,7 @@ struct WarpSolver {
             R zmin = R(INFINITY);
             R rq[4]; g_ld4(s_rq(), rq);
             for (int b = lane; b < dm.nb; b += 32) {
-              R v[4]; g_ld4(s_xp() + 4 * b, v);
+              R v[4]; g_ld4(s_xp() + PX * b, v);
               if (v[2] < zmin) zmin = v[2];
               if (io.ex.local_body_pos) {
                 R o[3]; q_rot_inv(rq, v, o);
