@@ -119,11 +119,13 @@ __device__ __forceinline__ bool no_normal_class(const int* q) {
   const long long nn = q[SQ_NNORM0] - ldv(q + SQ_LIVE_SLOW), ns = q[SQ_NSLOW0] + ldv(q + SQ_LIVE_SLOW);
   return 8 * nn < ns;
 }
-__device__ __forceinline__ bool slow_clip_critical(const int* q, int t_done) {
+// `margin` (frames): the clip stays critical until it is that far AHEAD of the bulk - the decision is only revisited at
+// segment boundaries, and a clip that falls behind between two of them ends the batch after the bulk.
+__device__ __forceinline__ bool slow_clip_critical(const int* q, int t_done, int margin) {
   const long long fn = ldv(q + SQ_FR_NORM), nn = q[SQ_NNORM0] - ldv(q + SQ_LIVE_SLOW);
   if (no_normal_class(q)) return false;
   if (fn <= 0) return true;
-  return (long long)t_done * nn < fn;
+  return (long long)(t_done - margin) * nn < fn;
 }
 // Sparse part of the grid: part_w warps on each of the first b_slow CTAs.  When the suspects do not fit into part_pct % of
 // the SMs at part_w per SM, there is no sparse part at all (b_slow = 0): so many slow clips are not a tail to protect but a
@@ -169,8 +171,9 @@ template <typename R, typename IO, int MAXWARPS>
 __global__ void __launch_bounds__(MAXWARPS * 32, 1)
 gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ GmrScal<R> ks,
                     const GmrConsts<R>* __restrict__ gconsts, const __grid_constant__ GmrIO<IO> io, uint32_t kflags,
-                    int* __restrict__ queue, const int* __restrict__ order, long long* __restrict__ rings, int part_w, int part_pct,
+                    int* __restrict__ queue, const int* __restrict__ order, long long* __restrict__ rings, int part_w, int part_pct_margin,
                     int seg_frames, double slow_err) {
+  const int part_pct = part_pct_margin & 0xff, crit_margin = part_pct_margin >> 8;     // (percentage | margin in frames << 8)
   extern __shared__ __align__(128) unsigned char gmr_dyn_smem[];
   unsigned char* const smem = gmr_dyn_smem;
   constexpr int CB = consts_bytes<R>();
@@ -308,7 +311,7 @@ gmr_retarget_kernel(const __grid_constant__ GmrDims dm, const __grid_constant__ 
       const bool took_slow = (w & W_TOOK_SLOW) != 0, resident = took_slow && (w & W_SLOW_BLOCK);
       if (!took_slow) atomicAdd(queue + SQ_FR_NORM, seg_frames);
       if (resident) {                                                  // refresh this clip's "critical" mark
-        const bool crit = nt >= 0 && slow_clip_critical(queue, nt);
+        const bool crit = nt >= 0 && slow_clip_critical(queue, nt, crit_margin);
         if (crit != ((w & W_CRITICAL) != 0)) { atomicAdd(n_crit, crit ? 1 : -1); w ^= W_CRITICAL; }
       }
       int T_c = io.T;
@@ -589,7 +592,10 @@ int launch(GmrModel* m, const GmrConsts<R>* dc, const float* pos, const float* q
     GmrIO<IO> iob = io;
     iob.t_begin = 1; iob.t_end = 0; iob.state = state;
     static const int pct_env = getenv("GMR_PARTITION_PCT") ? atoi(getenv("GMR_PARTITION_PCT")) : 50;
-    kern<<<grid, wpc * 32, smem, st>>>(dims, scal_of<R>(m), dc, iob, flags, q2, (const int*)nullptr, rings, part_env, pct_env, seg_env, slow_err_env);
+    // a slow clip stays critical until it is one segment ahead of the bulk (the decision is revisited once per segment)
+    static const int margin_env = getenv("GMR_CRIT_MARGIN") ? atoi(getenv("GMR_CRIT_MARGIN")) : -1;
+    const int margin = margin_env >= 0 ? (margin_env > 0xffff ? 0xffff : margin_env) : seg_env;
+    kern<<<grid, wpc * 32, smem, st>>>(dims, scal_of<R>(m), dc, iob, flags, q2, (const int*)nullptr, rings, part_env, pct_env | (margin << 8), seg_env, slow_err_env);
     CK(cudaGetLastError());
     g_launches.fetch_add(3);
     return GMR_OK;

@@ -700,6 +700,12 @@ struct WarpSolver {
         const R nsq = qe[1] * qe[1] + qe[2] * qe[2] + qe[3] * qe[3];
         R fac;
         if (nsq < ks.lie) fac = R(2) / qe[0] - R(2) / R(3) * nsq / (qe[0] * qe[0] * qe[0]);
+        else if (nsq < R(0.0025) * qe[0] * qe[0]) {
+          // theta / 2 = atan(t), t = n / w < 0.05 (a task that has nearly converged - the common case): 2 atan(t) / n =
+          // (2 / w) (1 - t^2/3 + t^4/5 - ...), truncated below 1e-22; the library atan2 is ~130 instructions
+          const R iw = R(1) / qe[0], t2 = nsq * iw * iw;
+          fac = R(2) * iw * (R(1) + t2 * (R(-1.0 / 3.0) + t2 * (R(1.0 / 5.0) + t2 * (R(-1.0 / 7.0) + t2 * (R(1.0 / 9.0) + t2 * (R(-1.0 / 11.0) + t2 * (R(1.0 / 13.0) + t2 * R(-1.0 / 15.0))))))));
+        }
         else { const R n = g_sqrt_pos(nsq); fac = R(2) * g_atan2(n, qe[0]) / n; }
         R om[3] = {fac * qe[1], fac * qe[2], fac * qe[3]};
         const R th2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
@@ -1127,14 +1133,13 @@ struct WarpSolver {
     GMR_LANES
       L.sacc = R(0);
     GMR_END_NOSYNC
-    for (int lv = dm.maxd; lv >= 1; lv--) {
+    {
       // slots [0, 5 + lv) = base + strict ancestors; the chunk count is a template argument so that shallow
-      // depths do not issue (predicated-off) work for slots they do not have
-      switch ((5 + lv + 3) >> 2) {
-        case 2: eliminate_depth<2>(lv, pinned); break;
-        case 3: eliminate_depth<3>(lv, pinned); break;
-        default: eliminate_depth<GMR_NS / 4>(lv, pinned); break;
-      }
+      // depths do not issue (predicated-off) work for slots they do not have: depths 8.. use 4 chunks, 4..7 three, 1..3 two
+      int lv = dm.maxd;
+      for (; lv >= 8; lv--) eliminate_depth<GMR_NS / 4>(lv, pinned);
+      for (; lv >= 4; lv--) eliminate_depth<3>(lv, pinned);
+      for (; lv >= 1; lv--) eliminate_depth<2>(lv, pinned);
     }
     if constexpr (sizeof(R) == 8) {
       // base block: S = A_bb - sum_k (1/d_k) h_k h_k^T,  b = b_b - sum_k (1/d_k) h_k y_k,  h_k = base slots of the
