@@ -130,10 +130,11 @@ template <typename R> GMR_HD int gmr_in_elems(int nhum) { return gmr_pad4((int)(
 //   [ mt: task blocks, MT nt | body poses, PX nb: (quat[4], pos[3], pad ..) ]   while FK / task evaluation are live, and
 //   [ published factor rows, nh * stride ]                                       from the factorisation to the next FK.
 // (body poses are dead once the composites are built; integrate() takes the root quaternion from GS_RQ.)
-template <typename R> GMR_HD constexpr int gmr_mt_elems(int nt) { return gmr_pad4(GmrLay<R>::MT * nt); }
+// task blocks; during FK the same region is the second pose buffer of the scan (ping-pong), hence at least PX * nb
+template <typename R> GMR_HD constexpr int gmr_mt_elems(int nt, int nb) { return gmr_pad4(GmrLay<R>::MT * nt > GmrLay<R>::PX * nb ? GmrLay<R>::MT * nt : GmrLay<R>::PX * nb); }
 template <typename R> GMR_HD constexpr int gmr_sd_elems(int nh) { return gmr_pad4(GmrLay<R>::SD * (nh > 0 ? nh : 1)); }
 template <typename R> GMR_HD int gmr_union_elems(int nb, int nh, int nt, int maxd) {
-  const int u = gmr_mt_elems<R>(nt) + gmr_pad4(GmrLay<R>::PX * nb);
+  const int u = gmr_mt_elems<R>(nt, nb) + gmr_pad4(GmrLay<R>::PX * nb);
   const int lr = (nh > 0 ? nh : 1) * gmr_row_stride<R>(maxd);
   return gmr_pad4(lr > u ? lr : u);
 }
@@ -145,7 +146,7 @@ template <typename R> GMR_HD int gmr_warp_elems(int nb, int nh, int nhum, int nt
 template <typename R> inline void gmr_dims_layout(GmrDims& d) {
   int o = GS_VAR;
   d.o_u = o;
-  d.o_xq = o + gmr_mt_elems<R>(d.nt);       // poses are one record of PX elements per body: orientation at +0, position at +4
+  d.o_xq = o + gmr_mt_elems<R>(d.nt, d.nb);       // poses are one record of PX elements per body: orientation at +0, position at +4
   d.o_xp = d.o_xq + 4;
   o += gmr_union_elems<R>(d.nb, d.nh, d.nt, d.maxd);
   d.o_sd = o; o += gmr_sd_elems<R>(d.nh);
@@ -499,6 +500,7 @@ struct WarpSolver {
   GMR_FN R* s_xp() const { return sm + dm.o_xp; }   // body poses: record b at PX * b, position here, orientation at s_xq
   GMR_FN R* s_xq() const { return sm + dm.o_xq; }
   GMR_FN R* s_U() const { return sm + GS_VAR; }
+  GMR_FN R* s_at(int off) const { return sm + off; }
   GMR_FN R* s_mt() const { return s_U(); }      // task inertias, dead once the rows are built
   GMR_FN R* s_L() const { return s_U(); }       // packed factor rows
   enum { ROWH = GmrLay<R>::ROWH, ROWS = GMR_NS + GmrLay<R>::ROWH };
@@ -530,8 +532,7 @@ struct WarpSolver {
   // starts from its pose in its moving parent's frame, (P, cos(q/2) A + sin(q/2) B), and in step k composes the pose its
   // ancestor at distance 2^k has accumulated so far in front of its own: after ceil(log2(depth + 1)) steps (4 for G1's 10
   // hinges + root) every lane holds its world pose - 4 dependent compositions on 30 lanes instead of 11 on 2-6.  The
-  // running pose stays in registers; each step reads the ancestor's from shared memory (one block) and publishes its
-  // own (next block).  Fixed bodies (hands, head, sensors: task frames and the epilogue need them) follow in one block.
+  // running pose stays in registers; each step reads the ancestors' poses from one buffer and publishes its own into the other.  Fixed bodies (hands, head, sensors: task frames and the epilogue need them) follow in one block.
   GMR_FN void fk() {
     R q[4] = {R(1), R(0), R(0), R(0)}, p[3] = {R(0), R(0), R(0)};
 #ifdef GMR_EMULATE
@@ -542,6 +543,12 @@ struct WarpSolver {
 #define GMR_FK_LOAD
 #define GMR_FK_SAVE
 #endif
+    // The scan ping-pongs between the pose array and the task-block region (dead during FK): a step reads one and writes the
+    // other, so it is ONE lane block (one __syncwarp) instead of a compose block and a publish block; the start buffer is
+    // chosen so that the last step lands in the pose array.
+    int nsteps = 0;
+    for (int k = 0; k < 4; k++) if ((1 << k) <= dm.maxd) nsteps++;      // a chain of maxd hinges + the root needs 2^K >= maxd + 1
+    int cur = (nsteps & 1) ? (int)GS_VAR : dm.o_xq;
     GMR_LANES
       if (lane < dm.nh) {
         R s, c; g_sincos(R(0.5) * s_q()[7 + lane], &s, &c);
@@ -549,29 +556,32 @@ struct WarpSolver {
         g_ld4(mc.fk_A + 4 * lane, A); g_ld4(mc.fk_B + 4 * lane, B); g_ld4(mc.fk_pos + 4 * lane, P);
         q[0] = c * A[0] + s * B[0]; q[1] = c * A[1] + s * B[1]; q[2] = c * A[2] + s * B[2]; q[3] = c * A[3] + s * B[3];
         p[0] = P[0]; p[1] = P[1]; p[2] = P[2];
-        const int b = mc.hbody[lane];
-        g_st4(s_xq() + PX * b, q[0], q[1], q[2], q[3]);
-        g_st4(s_xp() + PX * b, p[0], p[1], p[2], R(0));
+        R* o = s_at(cur) + PX * mc.hbody[lane];
+        g_st4(o, q[0], q[1], q[2], q[3]);
+        g_st4(o + 4, p[0], p[1], p[2], R(0));
       } else if (lane == dm.nh) {
         q[0] = s_q()[3]; q[1] = s_q()[4]; q[2] = s_q()[5]; q[3] = s_q()[6];
         q_normalize(q);
         p[0] = p[1] = p[2] = R(0);
-        g_st4(s_xq(), q[0], q[1], q[2], q[3]);
-        g_st4(s_xp(), R(0), R(0), R(0), R(0));
+        g_st4(s_at(cur), q[0], q[1], q[2], q[3]);
+        g_st4(s_at(cur) + 4, R(0), R(0), R(0), R(0));
         g_st4(s_rq(), q[0], q[1], q[2], q[3]);
       }
       GMR_FK_SAVE
     GMR_END
     GMR_NOUNROLL                                                      // one copy of the step in the instruction stream
-    for (int k = 0; k < 4; k++) {
-      if ((1 << k) <= dm.maxd) {                                        // a chain of maxd hinges + the root needs 2^K >= maxd + 1
-        GMR_LANES
-          GMR_FK_LOAD
+    for (int k = 0; k < nsteps; k++) {
+      const int nxt = cur == dm.o_xq ? (int)GS_VAR : dm.o_xq;
+      GMR_LANES
+        GMR_FK_LOAD
+        if (lane <= dm.nh) {
+          int b = 0;                                                    // the root (lane nh) only copies itself across
           if (lane < dm.nh) {
+            b = mc.hbody[lane];
             const int pb = (int)((mc.fk_idx[lane] >> (8 * k)) & 0xffu);
             if (pb != 0xff) {
               R pq[4], pp[4];
-              g_ld4(s_xq() + PX * pb, pq); g_ld4(s_xp() + PX * pb, pp);
+              g_ld4(s_at(cur) + PX * pb, pq); g_ld4(s_at(cur) + PX * pb + 4, pp);
               R off[3]; q_rot(pq, p, off);
               p[0] = pp[0] + off[0]; p[1] = pp[1] + off[1]; p[2] = pp[2] + off[2];
               R qn[4]; q_mul(pq, q, qn);
@@ -580,17 +590,13 @@ struct WarpSolver {
               q[0] = qn[0]; q[1] = qn[1]; q[2] = qn[2]; q[3] = qn[3];
             }
           }
-          GMR_FK_SAVE
-        GMR_END
-        GMR_LANES
-          GMR_FK_LOAD
-          if (lane < dm.nh && ((mc.fk_idx[lane] >> (8 * k)) & 0xffu) != 0xff) {
-            const int b = mc.hbody[lane];
-            g_st4(s_xq() + PX * b, q[0], q[1], q[2], q[3]);
-            g_st4(s_xp() + PX * b, p[0], p[1], p[2], R(0));
-          }
-        GMR_END
-      }
+          R* o = s_at(nxt) + PX * b;
+          g_st4(o, q[0], q[1], q[2], q[3]);
+          g_st4(o + 4, p[0], p[1], p[2], R(0));
+        }
+        GMR_FK_SAVE
+      GMR_END
+      cur = nxt;
     }
     GMR_LANES
       GMR_FK_LOAD
@@ -753,24 +759,35 @@ struct WarpSolver {
             Cq = (R(1) - th2 * R(0.5) - ct) / (th2 * th2);
             Dq = (R(2) * th - R(3) * st + th * ct) / (R(2) * th2 * th2 * th);
           }
+          // With W = [omega]x, V = [rho]x, wr = omega . rho, c = rho x omega:
+          //   W^2 = omega omega^T - theta^2 I,   V W = omega rho^T - wr I,   V W W = omega c^T - wr W,
+          // so Barfoot's Q = V/2 + Bq (W V + V W + W V W) - Cq (V W W - W W V - 3 W V W) - Dq (W V W W + W W V W), with
+          // W V W = -wr W and W V W W + W W V W = -2 wr W^2, is a symmetric part plus ONE skew matrix:
+          //   Q = Bq (omega rho^T + rho omega^T) - 2 Dq wr omega omega^T + 2 wr (Dq theta^2 - Bq) I  +  [a]x,
+          //   a = rho / 2 - (Bq + Cq) wr omega - Cq (c x omega)        (omega c^T - c omega^T = [c x omega]x)
+          // ~65 multiply-adds instead of two 3x3 products and a nine-entry combination.
           R S[9], S2[9], Ji[9];
-          m3_skew(om, S); m3_mul(S, S, S2);
+          m3_skew(om, S);
+          GMR_UNROLL
+          for (int i = 0; i < 3; i++) {
+            GMR_UNROLL
+            for (int j = 0; j < 3; j++) S2[3 * i + j] = om[i] * om[j] - (i == j ? th2 : R(0));
+          }
           GMR_UNROLL
           for (int i = 0; i < 9; i++) Ji[i] = ((i & 3) == 0 ? R(1) : R(0)) - R(0.5) * S[i] + cV * S2[i];
-          // Q(rho, omega) with W V W = -(omega.rho) W,  W V W W + W W V W = -2 (omega.rho) W^2
           R Q[9];
           {
-            R V[9], VW[9], VWW[9];
-            m3_skew(rho, V); m3_mul(V, S, VW); m3_mul(VW, S, VWW);
             const R wr = om[0] * rho[0] + om[1] * rho[1] + om[2] * rho[2];
+            const R c[3] = {rho[1] * om[2] - rho[2] * om[1], rho[2] * om[0] - rho[0] * om[2], rho[0] * om[1] - rho[1] * om[0]};
+            const R cw[3] = {c[1] * om[2] - c[2] * om[1], c[2] * om[0] - c[0] * om[2], c[0] * om[1] - c[1] * om[0]};
+            const R k1 = (Bq + Cq) * wr, k2 = R(2) * Dq * wr, kd = R(2) * wr * (Dq * th2 - Bq);
+            const R a[3] = {R(0.5) * rho[0] - k1 * om[0] - Cq * cw[0], R(0.5) * rho[1] - k1 * om[1] - Cq * cw[1], R(0.5) * rho[2] - k1 * om[2] - Cq * cw[2]};
+            R A[9]; m3_skew(a, A);
             GMR_UNROLL
             for (int i = 0; i < 3; i++) {
               GMR_UNROLL
-              for (int j = 0; j < 3; j++) {
-                const int ij = 3 * i + j, ji = 3 * j + i;
-                const R wvw = -wr * S[ij];
-                Q[ij] = R(0.5) * V[ij] + Bq * (VW[ji] + VW[ij] + wvw) - Cq * (VWW[ij] - VWW[ji] - R(3) * wvw) - Dq * R(2) * wr * S2[ij];
-              }
+              for (int j = 0; j < 3; j++)
+                Q[3 * i + j] = Bq * (om[i] * rho[j] + om[j] * rho[i]) - k2 * (om[i] * om[j]) + (i == j ? kd : R(0)) + A[3 * i + j];
             }
           }
           if (th2 < ks.lie) {
