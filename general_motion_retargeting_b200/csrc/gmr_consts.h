@@ -11,6 +11,7 @@
 #define GMR_MAX_LEVEL 64
 #define GMR_MAXD 10          // deepest chain of hinges root -> leaf the factorisation is unrolled for (G1: 10)
 #define GMR_NS (6 + GMR_MAXD) // row slots of one hinge: 6 floating-base columns, then its ancestors by depth
+#define GMR_ANCS 12          // bytes per row of the ancestor table (GMR_MAXD rounded up to whole words)
 
 template <typename R>
 struct GmrConsts {
@@ -38,7 +39,9 @@ struct GmrConsts {
   int32_t maxd, tlmax, _pad2[2];      // deepest hinge chain; most tasks in any hinge's subtree
   uint32_t lvl_mask[GMR_MAXD + 2];    // [d] -> bitmask of the hinges of depth d (1-based)
   uint8_t hdepth[GMR_NH];             // hinge i -> number of hinges on the chain root .. i (inclusive); 0 for unused lanes
-  uint8_t anc_of[GMR_NH * GMR_MAXD];  // [i][d-1] -> the hinge at depth d on i's chain (d <= hdepth[i]; own index at d = hdepth[i])
+  // [i][d-1] -> the hinge at depth d on i's chain (d <= hdepth[i]; own index from d = hdepth[i] on); rows of GMR_ANCS = 12 bytes,
+  // 4-byte aligned: a lane fetches its whole row as three words
+  alignas(4) uint8_t anc_of[GMR_NH * GMR_ANCS];
   // Forward-kinematics records.  FK is a pointer-jumping scan over the tree of MOVING bodies (hinge bodies + the root):
   // fixed bodies between two hinges are folded into constants on the host.
   //   entries [0, nh): hinge j.  Its body's pose in the frame of its nearest moving ancestor is
@@ -159,8 +162,8 @@ inline int gmr_fill_consts(const GmrModelDesc* d, GmrConsts<R>* c, const char** 
     if (n > GMR_MAXD) return fail(GMR_ELIMIT, "hinge chain too deep (GMR_MAXD)");
     m.hdepth[j] = (uint8_t)n;
     if (n > m.maxd) m.maxd = n;
-    for (int d = 1; d <= n; d++) m.anc_of[j * GMR_MAXD + d - 1] = (uint8_t)chain[n - d];
-    for (int d = n + 1; d <= GMR_MAXD; d++) m.anc_of[j * GMR_MAXD + d - 1] = (uint8_t)j;
+    for (int d = 1; d <= n; d++) m.anc_of[j * GMR_ANCS + d - 1] = (uint8_t)chain[n - d];
+    for (int d = n + 1; d <= GMR_ANCS; d++) m.anc_of[j * GMR_ANCS + d - 1] = (uint8_t)j;
     for (int i = 0; i < m.nh; i++) if ((m.anc_mask[j] >> i) & 1u) m.desc_mask[i] |= 1u << j;
   }
   for (int j = 0; j < m.nh; j++) m.lvl_mask[m.hdepth[j]] |= 1u << j;

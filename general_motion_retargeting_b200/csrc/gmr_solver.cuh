@@ -959,7 +959,7 @@ struct WarpSolver {
         static_assert(GMR_MAXD == 10, "the depth split below assumes ten slots");
         GMR_UNROLL
         for (int d = 1; d <= 6; d++) {
-          const int j = mc.anc_of[lane * GMR_MAXD + d - 1];
+          const int j = mc.anc_of[lane * GMR_ANCS + d - 1];
           R s[6]; g_ld4(s_sd() + SD * j, s); g_ld2(s_sd() + SD * j + 4, s + 4);
           const R t = f[0] * s[0] + f[1] * s[1] + f[2] * s[2] + f[3] * s[3] + f[4] * s[4] + f[5] * s[5];
           L.row[5 + d] = d < dep ? t : R(0);
@@ -967,7 +967,7 @@ struct WarpSolver {
         if (dm.maxd > 7) {                                       // uniform
           GMR_UNROLL
           for (int d = 7; d < GMR_MAXD; d++) {
-            const int j = mc.anc_of[lane * GMR_MAXD + d - 1];
+            const int j = mc.anc_of[lane * GMR_ANCS + d - 1];
             R s[6]; g_ld4(s_sd() + SD * j, s); g_ld2(s_sd() + SD * j + 4, s + 4);
             const R t = f[0] * s[0] + f[1] * s[1] + f[2] * s[2] + f[3] * s[3] + f[4] * s[4] + f[5] * s[5];
             L.row[5 + d] = d < dep ? t : R(0);
@@ -1025,7 +1025,7 @@ struct WarpSolver {
         R r = L.rhs;
         GMR_UNROLL
         for (int d = 1; d < GMR_MAXD; d++) {                      // pinned ancestors: my own slots
-          const int j = mc.anc_of[lane * GMR_MAXD + d - 1];
+          const int j = mc.anc_of[lane * GMR_ANCS + d - 1];
           const bool pj = d < dep && ((pinned >> j) & 1u);
           const R t = r - L.row[5 + d] * s_bnd()[j];              // s_bnd of an unpinned hinge is stale: computed, not selected
           r = pj ? t : r;
@@ -1228,30 +1228,58 @@ struct WarpSolver {
         for (int i = 0; i < 6; i++) s_xs()[i] = x[i];
       }
     GMR_END
-    // back substitution, root -> leaves:  x_k = (y_k - sum_s row_k[s] x_(anc at slot s)) / d_k
-    GMR_LANES
-      if (lane < dm.nh) {
+    // back substitution, root -> leaves:  x_k = (y_k - sum_s row_k[s] x_(anc at slot s)) / d_k.  The ancestors' values travel by
+    // warp shuffle (each lane names its ancestor at the level's depth; a lane that has none names itself and discards the
+    // value): one multiply, one shuffle and one FMA per level instead of a store, a __syncwarp, a table look-up and a load.
+    {
+#ifdef GMR_EMULATE
+      R xv[32], xmine[32];
+      for (int i = 0; i < 32; i++) xmine[i] = R(0);
+#else
+      R xmine = R(0);
+#endif
+#ifndef GMR_EMULATE
+      uint32_t aw[3];                                           // this lane's ancestors by depth, one byte each
+#endif
+      GMR_LANES
         R acc = L.rhs;
         GMR_UNROLL
         for (int c = 0; c < 6; c++) acc -= L.row[c] * s_xs()[c];
         L.rhs = acc;
-      }
-    GMR_END_NOSYNC
-    GMR_UNROLL
-    for (int lv = 1; lv <= GMR_MAXD; lv++) {
-      if (lv <= dm.maxd) {
-        GMR_LANES
-          if (GMR_DEPTH == lv) s_xs()[6 + lane] = L.rhs * L.dinv;
-        GMR_END
-        if (lv < dm.maxd) {
+#ifndef GMR_EMULATE
+        const uint32_t* ap = reinterpret_cast<const uint32_t*>(mc.anc_of + lane * GMR_ANCS);
+        aw[0] = ap[0]; aw[1] = ap[1]; aw[2] = ap[2];
+#endif
+      GMR_END_NOSYNC
+      GMR_UNROLL
+      for (int lv = 1; lv <= GMR_MAXD; lv++) {
+        if (lv <= dm.maxd) {
+#ifdef GMR_EMULATE
           GMR_LANES
-            if (GMR_DEPTH > lv) {
-              const int j = mc.anc_of[lane * GMR_MAXD + lv - 1];
-              L.rhs -= L.row[5 + lv] * s_xs()[6 + j];
-            }
+            xv[lane] = L.rhs * L.dinv;
+            if (GMR_DEPTH == lv) xmine[lane] = xv[lane];
           GMR_END_NOSYNC
+          GMR_LANES
+            const R xa = xv[mc.anc_of[lane * GMR_ANCS + lv - 1]];
+            if (GMR_DEPTH > lv) L.rhs -= L.row[5 + lv] * xa;
+          GMR_END_NOSYNC
+#else
+          GMR_LANES
+            const R x = L.rhs * L.dinv;                             // final on the lanes of depth lv
+            xmine = GMR_DEPTH == lv ? x : xmine;
+            const R xa = __shfl_sync(0xffffffffu, x, (int)((aw[(lv - 1) >> 2] >> (8 * ((lv - 1) & 3))) & 0xffu));
+            L.rhs = GMR_DEPTH > lv ? L.rhs - L.row[5 + lv] * xa : L.rhs;
+          GMR_END_NOSYNC
+#endif
         }
       }
+      GMR_LANES
+#ifdef GMR_EMULATE
+        if (lane < dm.nh) s_xs()[6 + lane] = xmine[lane];
+#else
+        if (lane < dm.nh) s_xs()[6 + lane] = xmine;
+#endif
+      GMR_END
     }
   }
 
@@ -1379,7 +1407,7 @@ struct WarpSolver {
           GMR_UNROLL
           for (int f = 0; f < 6; f++) g += L.row[f] * s_xs()[f];
           GMR_UNROLL
-          for (int d = 1; d < GMR_MAXD; d++) g += L.row[5 + d] * s_xs()[6 + mc.anc_of[lane * GMR_MAXD + d - 1]];
+          for (int d = 1; d < GMR_MAXD; d++) g += L.row[5 + d] * s_xs()[6 + mc.anc_of[lane * GMR_ANCS + d - 1]];
           g += sum_over_bits(mine ? GMR_DESC : 0u, [&](int k) { return Lrow(k)[5 + dep]; });
           if (lane < dm.nh) s_red()[lane] = mine ? (((pin_lo >> lane) & 1u) ? g : -g) : INF;
         }
