@@ -1353,6 +1353,9 @@ struct WarpSolver {
           R alpha = R(1); int blk = -1;
 #ifdef GMR_EMULATE
           for (int j = 0; j < dm.nh; j++) { const R a = s_red()[j]; if (a < alpha) { alpha = a; blk = j; } }
+#ifdef GMR_STATS
+          { int nb_ = 0; for (int j = 0; j < dm.nh; j++) if (s_red()[j] < R(1)) nb_++; GMR_STAT(9, nb_); if (nb_ >= 2) GMR_STAT(10, 1); }
+#endif
 #else
           {   // smallest step and the lowest hinge that attains it: butterfly min + ballot
             const R mine = lane_ < dm.nh ? s_red()[lane_] : R(INFINITY);
