@@ -72,7 +72,7 @@ struct GmrDims {
   // per-warp shared-memory layout for the launching precision (element offsets, see gmr_solver.cuh)
   int32_t o_tg, o_in, o_xp, o_xq, o_u, warp_elems;
   int32_t o_y, rs;            // published factor row of a hinge: header (y, 1/d), then slots [0, o_y); stride rs elements
-  int32_t o_sd, rs_b;         // spatial axes; row stride in bytes
+  int32_t o_sd, _pad_dims;    // spatial axes
 };
 // `lie`: the reference's small-angle threshold (GmrModelDesc.lie_eps), the same float64-derived value in both precisions:
 // the branch decisions (Taylor vs closed form, the jlog = I shortcut) must follow the float64 reference, not the kernel's dtype
@@ -84,7 +84,7 @@ template <typename R> inline GmrDims gmr_dims_of(const GmrConsts<R>& c) {
   d.use1 = c.use1; d.use2 = c.use2; d.max_iter = c.max_iter;
   d.in1_mask = c.in1_mask; d.in2_mask = c.in2_mask; d.limited_mask = c.limited_mask; d.foot_mask = c.foot_mask;
   d.maxd = c.maxd; d.tlmax = c.tlmax;
-  d.o_tg = d.o_in = d.o_xp = d.o_xq = d.o_u = d.warp_elems = d.o_y = d.rs = d.o_sd = d.rs_b = 0;
+  d.o_tg = d.o_in = d.o_xp = d.o_xq = d.o_u = d.warp_elems = d.o_y = d.rs = d.o_sd = d._pad_dims = 0;
   return d;
 }
 template <typename R> inline GmrScal<R> gmr_scal_of(const GmrConsts<R>& c) {
