@@ -69,6 +69,26 @@ extern "C" int gmr_emu_retarget_batch_ex(const GmrModelDesc* d, const float* pos
 }
 
 // order in which the emulator visits the lanes of a block (a permutation of 0..31; not thread safe: set it between runs)
+// Per-warp shared-memory layout of precision `bits` for a model: out[0..15] = { GS_VAR, o_u, o_xq, o_xp, o_sd, o_tg, o_in,
+// warp_elems, PX, SD, TG, MT, row stride, ROWH, consts bytes, sizeof(R) } (tests/test_emulator.py checks alignment, bank-friendly
+// strides, disjoint regions and the 16-warp budget the float64 kernel relies on for G1).
+template <typename R> static int layout(const GmrModelDesc* d, int32_t* out) {
+  auto* mc = new GmrConsts<R>();
+  const char* why = nullptr;
+  int rc = gmr_fill_consts<R>(d, mc, &why);
+  if (rc != GMR_OK) { delete mc; return rc; }
+  GmrDims dm = gmr_dims_of(*mc);
+  gmr_dims_layout<R>(dm);
+  const int32_t v[16] = {GS_VAR, dm.o_u, dm.o_xq, dm.o_xp, dm.o_sd, dm.o_tg, dm.o_in, dm.warp_elems, GmrLay<R>::PX, GmrLay<R>::SD,
+                         GmrLay<R>::TG, GmrLay<R>::MT, dm.rs, GmrLay<R>::ROWH, (int32_t)((sizeof(GmrConsts<R>) + 15) / 16 * 16), (int32_t)sizeof(R)};
+  for (int i = 0; i < 16; i++) out[i] = v[i];
+  delete mc;
+  return GMR_OK;
+}
+extern "C" int gmr_emu_layout(const GmrModelDesc* d, int32_t precision_bits, int32_t* out) {
+  return precision_bits == 32 ? layout<float>(d, out) : layout<double>(d, out);
+}
+
 extern "C" int gmr_emu_set_lane_order(const int* order) {
   bool seen[32] = {};
   for (int i = 0; i < 32; i++) { if (order[i] < 0 || order[i] > 31 || seen[order[i]]) return -1; seen[order[i]] = true; }

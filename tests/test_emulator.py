@@ -215,3 +215,34 @@ def test_lane_blocks_do_not_depend_on_the_lane_order(built, bits):
         for x, y in zip(results[0], r):
             np.testing.assert_array_equal(np.asarray(x), np.asarray(y))
     assert helpers._emu.gmr_emu_set_lane_order((C.c_int * 32)(*([0] * 32))) == -1         # not a permutation
+
+
+@pytest.mark.parametrize("src,robot", [("smplx", "unitree_g1"), ("bvh", "booster_t1"), ("smplx", "hightorque_hi"), ("smplx", "stanford_toddy")])
+@pytest.mark.parametrize("bits", [64, 32])
+def test_shared_memory_layout_is_aligned_and_bank_friendly(src, robot, bits):
+    """The per-warp working set: every region 16-byte aligned (128-bit accesses), regions disjoint, the records
+    that consecutive lanes touch at strides that are ODD in 16-byte units (a quarter-warp's 128-bit access is then one
+    wavefront), the task-block region large enough to be the FK scan's second pose buffer, the factor rows inside the union -
+    and, for G1 in float64, 16 warps per CTA within the 227 KB a B200 SM offers (the occupancy the headline numbers rest on)."""
+    import ctypes as C
+    from general_motion_retargeting_b200._native import build_desc
+    import helpers
+    m, tt, _ = helpers.problem(src, robot)
+    c0 = make_clips(m, tt, [0], T=1)
+    helpers.emu_retarget_batch(m, tt, c0.pos, c0.quat, c0.ratio(tt), bits=bits)   # loads the library
+    desc, keep = build_desc(m, tt)
+    out = (C.c_int32 * 16)()
+    assert helpers._emu.gmr_emu_layout(C.byref(desc), bits, out) == 0
+    gs_var, o_u, o_xq, o_xp, o_sd, o_tg, o_in, wel, PX, SD, TG, MT, rs, rowh, cbytes, esz = list(out)
+    per16 = 16 // esz                                                       # elements per 16-byte unit
+    for off in (gs_var, o_u, o_xq, o_xp, o_sd, o_tg, o_in, wel):
+        assert off % per16 == 0, "region not 16-byte aligned"
+    for stride in (PX, MT, rs) + ((SD, TG) if bits == 64 else ()):
+        assert stride % per16 == 0 and (stride // per16) % 2 == 1, f"stride {stride} is not odd in 16-byte units"
+    nb, nh, nt, nhum = m.nbody, m.nhinge, tt.nt, tt.nh
+    assert o_u == gs_var and o_xp == o_xq + 4
+    assert o_xq - o_u >= max(MT * nt, PX * nb)                               # task blocks; also the scan's second pose buffer
+    assert o_sd >= o_xq + PX * nb and o_sd >= o_u + rowh + rs * nh - rowh    # poses and factor rows end inside the union
+    assert o_tg >= o_sd + SD * nh and o_in >= o_tg + TG * nhum and wel > o_in
+    if robot == "unitree_g1" and bits == 64:
+        assert 16 + cbytes + 16 * wel * esz <= 232448, "G1 float64 no longer fits 16 warps per CTA"
